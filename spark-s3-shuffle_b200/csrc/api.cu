@@ -1,0 +1,1206 @@
+// api.cu — runtime + C ABI of libb200shuffle.so (see include/b200shuffle.h for the contract and the reference
+// interfaces each entry point replaces).
+//
+// Structure: a process-wide context with one Device per selected GPU.  A Device owns NSLOT pipeline slots; a slot is
+// a CUDA stream plus grow-only device buffers (staged source/destination arenas, descriptor "meta" block, codec
+// scratch) and a pinned host block for descriptor traffic.  Host-pointer entry points cut a batch into chunks of
+// ~64 MiB, and run H2D -> kernels -> (size readback) -> D2H per chunk on rotating slots so copies of one chunk
+// overlap kernels of another.  "_dev" entry points run the same kernel sequence on caller-owned device arenas.
+// There is no CPU fallback anywhere in this file: without a device every compute entry point fails with B2S_E_CUDA.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace b2s;
+
+namespace {
+
+thread_local std::string t_last_error;
+thread_local b2s_timing t_timing;
+
+int fail(int code, const char* fmt, const char* a = "") {
+  char buf[512];
+  snprintf(buf, sizeof buf, fmt, a);
+  t_last_error = buf;
+  return code;
+}
+int fail_cuda(const char* what, cudaError_t e) {
+  t_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return B2S_E_CUDA;
+}
+#define CU(call)                                           \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) return fail_cuda(#call, e__);  \
+  } while (0)
+
+constexpr int NSLOT = 3;
+constexpr uint64_t kChunkBytes = 64ull << 20;
+constexpr uint32_t kChunkStreams = 1u << 18;
+constexpr uint32_t kXxhSeed = 0x9747b28cu;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = align_up(bytes + bytes / 8, 1 << 20);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(B2S_E_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = align_up(bytes + bytes / 4, 1 << 16);
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(B2S_E_NOMEM, "cudaHostAlloc: %s", cudaGetErrorString(e));
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// bump allocator over one buffer
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base((uint8_t*)b) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 16);
+    T* r = (T*)(base + off);
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;              // readback milestones
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;            // kernel region
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;            // dominant kernel
+  cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;  // copies
+  DevBuf meta, scratch, desc, src, dst;
+  PinBuf hmeta;
+};
+
+struct Device {
+  int ordinal = 0;
+  Slot slot[NSLOT];
+  ChecksumTables tabs{};
+  std::mutex mtx;
+};
+
+struct Context {
+  std::vector<Device*> devs;
+  std::atomic<uint64_t> launches{0};
+};
+Context* g_ctx = nullptr;
+std::mutex g_init_mtx;
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+uint32_t block_size_or_default(uint32_t codec, uint32_t bs) {
+  (void)codec;
+  return bs ? bs : 32768u;
+}
+
+// pick the checksum work-item size: enough items to fill the machine, big enough to amortise the combine
+uint32_t pick_tile_shift(uint64_t total_bytes) {
+  uint32_t s = 20;  // 1 MiB
+  const uint64_t want_items = (uint64_t)kSMs * 32 * 4;
+  while (s > 14 && (total_bytes >> s) < want_items) s--;
+  return s;
+}
+
+double ms_between(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return 0;
+  return ms;
+}
+
+struct WallTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// --------------------------------------------------------------------------------------------------------------
+// compress job: one chunk of n streams living in a device source arena
+// --------------------------------------------------------------------------------------------------------------
+struct CompressJob {
+  uint32_t n = 0, nb = 0;
+  // pinned host mirror
+  uint64_t *h_src_off = nullptr, *h_src_len = nullptr;
+  uint32_t* h_blk_base = nullptr;
+  uint64_t *h_dst_off = nullptr, *h_dst_len = nullptr, *h_cks = nullptr, *h_total = nullptr;
+  int32_t* h_status = nullptr;
+  size_t up_bytes = 0, down_bytes = 0;
+  uint8_t *d_up = nullptr, *d_down = nullptr;
+  uint8_t *h_up = nullptr, *h_down = nullptr;
+};
+
+// lays out pinned + device meta for a compress chunk; returns 0 or error
+int compress_prepare(Slot& S, uint32_t codec, uint32_t bs, uint32_t n, const uint64_t* src_len, CompressJob& J) {
+  if (codec != B2S_CODEC_LZ4BLOCK) return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", "");
+  if (bs < 64 || bs > 65536) return fail(B2S_E_UNSUPPORTED, "lz4 block size must be in [64, 65536]%s");
+  J.n = n;
+  uint64_t nb = 0;
+  for (uint32_t i = 0; i < n; i++) nb += (src_len[i] + bs - 1) / bs;
+  if (nb >= 0x7fffffffull) return fail(B2S_E_ARG, "too many codec blocks in one chunk%s");
+  J.nb = (uint32_t)nb;
+  // pinned: upload [src_off | src_len | blk_base], download [dst_off | dst_len | cks | total | status]
+  size_t up = align_up(n * 8, 16) * 2 + align_up((n + 1) * 4, 16);
+  size_t down = align_up(n * 8, 16) * 3 + 16 + align_up(n * 4, 16);
+  int rc = S.hmeta.ensure(up + down + 64);
+  if (rc) return rc;
+  Carver hc(S.hmeta.p);
+  J.h_up = (uint8_t*)hc.take<uint64_t>(0);
+  J.h_src_off = hc.take<uint64_t>(n);
+  J.h_src_len = hc.take<uint64_t>(n);
+  J.h_blk_base = hc.take<uint32_t>(n + 1);
+  hc.off = align_up(hc.off, 16);
+  J.up_bytes = hc.off;
+  J.h_down = (uint8_t*)hc.take<uint64_t>(0);
+  size_t d0 = hc.off;
+  J.h_dst_off = hc.take<uint64_t>(n);
+  J.h_dst_len = hc.take<uint64_t>(n);
+  J.h_cks = hc.take<uint64_t>(n);
+  J.h_total = hc.take<uint64_t>(2);
+  J.h_status = hc.take<int32_t>(n);
+  hc.off = align_up(hc.off, 16);
+  J.down_bytes = hc.off - d0;
+  return 0;
+}
+
+struct CompressDevMeta {
+  uint64_t *src_off, *src_len;
+  uint32_t* blk_base;
+  uint64_t *dst_off, *dst_len, *cks, *total;
+  int32_t* status;
+  uint32_t *csize, *hash;
+  uint64_t *sizes, *work_base, *ws;
+  unsigned int* counter;
+};
+
+int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t bs, uint32_t alg, CompressJob& J,
+                     const uint8_t* d_src, uint8_t* d_dst, uint64_t dst_cap, CompressDevMeta& M, uint64_t* launches) {
+  const uint32_t n = J.n, nb = J.nb;
+  size_t ws_elems = std::max(scan_ws_elems(nb + 1), checksum_ws_elems(n)) + 4;
+  size_t need = J.up_bytes + J.down_bytes + align_up((size_t)nb * 4, 16) * 2 + align_up(((size_t)nb + 1) * 8, 16) +
+                align_up(((size_t)n + 1) * 8, 16) + ws_elems * 8 + 256;
+  int rc = S.meta.ensure(need);
+  if (rc) return rc;
+  rc = S.scratch.ensure((size_t)nb * bs + 64);
+  if (rc) return rc;
+  Carver dc(S.meta.p);
+  J.d_up = (uint8_t*)dc.take<uint64_t>(0);
+  M.src_off = dc.take<uint64_t>(n);
+  M.src_len = dc.take<uint64_t>(n);
+  M.blk_base = dc.take<uint32_t>(n + 1);
+  dc.off = align_up(dc.off, 16);
+  J.d_down = (uint8_t*)dc.take<uint64_t>(0);
+  M.dst_off = dc.take<uint64_t>(n);
+  M.dst_len = dc.take<uint64_t>(n);
+  M.cks = dc.take<uint64_t>(n);
+  M.total = dc.take<uint64_t>(2);
+  M.status = dc.take<int32_t>(n);
+  M.csize = dc.take<uint32_t>(nb);
+  M.hash = dc.take<uint32_t>(nb);
+  M.sizes = dc.take<uint64_t>((size_t)nb + 1);
+  M.work_base = dc.take<uint64_t>((size_t)n + 1);
+  M.ws = dc.take<uint64_t>(ws_elems);
+  M.counter = dc.take<unsigned int>(4);
+
+  // blk_base prefix on the host
+  uint64_t acc = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    J.h_blk_base[i] = (uint32_t)acc;
+    acc += (J.h_src_len[i] + bs - 1) / bs;
+  }
+  J.h_blk_base[n] = (uint32_t)acc;
+
+  cudaStream_t st = S.st;
+  CU(cudaMemcpyAsync(J.d_up, J.h_up, J.up_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(J.d_down, 0, J.down_bytes, st));
+  CU(cudaEventRecord(S.ev_k0, st));
+  launch_xxh32_encode(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, kXxhSeed, M.hash, st, launches);
+  CU(cudaEventRecord(S.ev_t0, st));
+  launch_lz4_compress(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, (uint8_t*)S.scratch.p, M.csize, M.sizes,
+                      M.counter, st, launches);
+  CU(cudaEventRecord(S.ev_t1, st));
+  launch_exclusive_scan_u64(M.sizes, nb, M.total, M.ws, st, launches);
+  launch_lz4block_pack(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, (const uint8_t*)S.scratch.p, M.csize,
+                       M.hash, M.sizes, M.total, d_dst, dst_cap, M.dst_off, M.dst_len, M.status, st, launches);
+  if (alg != B2S_CHECKSUM_NONE) {
+    uint32_t shift = pick_tile_shift(dst_cap < (uint64_t)nb * bs ? dst_cap : (uint64_t)nb * bs);
+    launch_checksum(tabs, alg, d_dst, M.dst_off, M.dst_len, n, shift, M.work_base, M.ws, M.cks, st, launches);
+  }
+  CU(cudaEventRecord(S.ev_k1, st));
+  CU(cudaMemcpyAsync(J.h_down, J.d_down, J.down_bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(S.ev_a, st));
+  CU(cudaGetLastError());
+  (void)C;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// decompress job
+// --------------------------------------------------------------------------------------------------------------
+struct DecompressJob {
+  uint32_t n = 0, n_slices = 0;
+  uint64_t nb = 0, total_out = 0;
+  uint64_t *h_src_off = nullptr, *h_src_len = nullptr;
+  uint64_t *h_slice_off = nullptr, *h_slice_len = nullptr, *h_slice_sum = nullptr;
+  uint32_t *h_slice_owner = nullptr, *h_slice_base = nullptr;
+  uint64_t* h_totals = nullptr;  // [nb_total, olen_total]
+  uint64_t *h_dst_off = nullptr, *h_dst_len = nullptr;
+  int32_t *h_status = nullptr, *h_bad = nullptr;
+  size_t up_bytes = 0, down_bytes = 0;
+  uint8_t *h_up = nullptr, *h_down = nullptr, *d_up = nullptr, *d_down = nullptr;
+  // device
+  uint64_t *src_off = nullptr, *src_len = nullptr, *slice_off = nullptr, *slice_len = nullptr, *slice_sum = nullptr;
+  uint32_t *slice_owner = nullptr, *slice_base = nullptr;
+  uint64_t *nblk = nullptr, *olen = nullptr, *dst_off = nullptr, *totals = nullptr, *cks_got = nullptr,
+           *work_base = nullptr, *ws = nullptr;
+  int32_t *status = nullptr, *bad = nullptr;
+  unsigned int* counter = nullptr;
+};
+
+int decompress_prepare(Slot& S, uint32_t codec, uint32_t alg, uint32_t n, uint32_t n_slices, DecompressJob& J) {
+  if (codec != B2S_CODEC_LZ4BLOCK) return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", "");
+  J.n = n;
+  J.n_slices = alg ? n_slices : 0;
+  const uint32_t s = J.n_slices;
+  size_t up = align_up(n * 8, 16) * 2 + align_up((size_t)s * 8, 16) * 3 + align_up((size_t)s * 4, 16) +
+              align_up(((size_t)n + 1) * 4, 16);
+  size_t down = 32 + align_up(n * 8, 16) * 2 + align_up(n * 4, 16) * 2;
+  int rc = S.hmeta.ensure(up + down + 128);
+  if (rc) return rc;
+  Carver hc(S.hmeta.p);
+  J.h_up = (uint8_t*)hc.take<uint64_t>(0);
+  J.h_src_off = hc.take<uint64_t>(n);
+  J.h_src_len = hc.take<uint64_t>(n);
+  J.h_slice_off = hc.take<uint64_t>(s);
+  J.h_slice_len = hc.take<uint64_t>(s);
+  J.h_slice_sum = hc.take<uint64_t>(s);
+  J.h_slice_owner = hc.take<uint32_t>(s);
+  J.h_slice_base = hc.take<uint32_t>((size_t)n + 1);
+  hc.off = align_up(hc.off, 16);
+  J.up_bytes = hc.off;
+  J.h_down = (uint8_t*)hc.take<uint64_t>(0);
+  size_t d0 = hc.off;
+  J.h_totals = hc.take<uint64_t>(4);
+  J.h_dst_off = hc.take<uint64_t>(n);
+  J.h_dst_len = hc.take<uint64_t>(n);
+  J.h_status = hc.take<int32_t>(n);
+  J.h_bad = hc.take<int32_t>(n);
+  hc.off = align_up(hc.off, 16);
+  J.down_bytes = hc.off - d0;
+  return 0;
+}
+
+// phase A: checksum verify + header count + scans + totals readback
+int decompress_enqueue_a(Slot& S, const ChecksumTables& tabs, uint32_t alg, DecompressJob& J, const uint8_t* d_src,
+                         uint64_t src_bytes, uint64_t* launches) {
+  const uint32_t n = J.n, s = J.n_slices;
+  size_t ws_elems = std::max(scan_ws_elems((size_t)n + 1), checksum_ws_elems(s)) + 4;
+  size_t need = J.up_bytes + J.down_bytes + align_up((size_t)n * 8, 16) * 1 + align_up((size_t)s * 8, 16) +
+                align_up(((size_t)s + 1) * 8, 16) + ws_elems * 8 + 256;
+  int rc = S.meta.ensure(need);
+  if (rc) return rc;
+  Carver dc(S.meta.p);
+  J.d_up = (uint8_t*)dc.take<uint64_t>(0);
+  J.src_off = dc.take<uint64_t>(n);
+  J.src_len = dc.take<uint64_t>(n);
+  J.slice_off = dc.take<uint64_t>(s);
+  J.slice_len = dc.take<uint64_t>(s);
+  J.slice_sum = dc.take<uint64_t>(s);
+  J.slice_owner = dc.take<uint32_t>(s);
+  J.slice_base = dc.take<uint32_t>((size_t)n + 1);
+  dc.off = align_up(dc.off, 16);
+  J.d_down = (uint8_t*)dc.take<uint64_t>(0);
+  J.totals = dc.take<uint64_t>(4);
+  J.dst_off = dc.take<uint64_t>(n);
+  J.olen = dc.take<uint64_t>(n);
+  J.status = dc.take<int32_t>(n);
+  J.bad = dc.take<int32_t>(n);
+  J.nblk = dc.take<uint64_t>(n);
+  J.cks_got = dc.take<uint64_t>(s);
+  J.work_base = dc.take<uint64_t>((size_t)s + 1);
+  J.ws = dc.take<uint64_t>(ws_elems);
+  J.counter = dc.take<unsigned int>(4);
+
+  cudaStream_t st = S.st;
+  CU(cudaMemcpyAsync(J.d_up, J.h_up, J.up_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(J.d_down, 0, J.down_bytes, st));
+  CU(cudaMemsetAsync(J.bad, 0xff, (size_t)n * 4, st));
+  CU(cudaEventRecord(S.ev_k0, st));
+  if (alg != B2S_CHECKSUM_NONE && s) {
+    launch_checksum(tabs, alg, d_src, J.slice_off, J.slice_len, s, pick_tile_shift(src_bytes), J.work_base, J.ws,
+                    J.cks_got, st, launches);
+    launch_checksum_compare(J.cks_got, J.slice_sum, J.slice_owner, J.slice_base, s, J.status, J.bad, st, launches);
+  }
+  launch_lz4block_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.status, st, launches);
+  // dst_off = exclusive scan(olen) ; blk_base = exclusive scan(nblk) (in place)
+  CU(cudaMemcpyAsync(J.dst_off, J.olen, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  launch_exclusive_scan_u64(J.dst_off, n, J.totals + 1, J.ws, st, launches);
+  launch_exclusive_scan_u64(J.nblk, n, J.totals + 0, J.ws, st, launches);
+  CU(cudaMemcpyAsync(J.h_totals, J.totals, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(S.ev_a, st));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// phase B (after ev_a): descriptors, decode, XXH32 verify, meta readback
+int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_t* d_dst, uint64_t dst_cap,
+                         uint64_t* launches) {
+  J.nb = J.h_totals[0];
+  J.total_out = J.h_totals[1];
+  if (J.nb >= 0xffffffffull) return fail(B2S_E_ARG, "too many codec blocks in one chunk%s");
+  int rc = S.desc.ensure((size_t)(J.nb + 1) * sizeof(BlockDesc));
+  if (rc) return rc;
+  cudaStream_t st = S.st;
+  BlockDesc* desc = (BlockDesc*)S.desc.p;
+  CU(cudaMemsetAsync(desc, 0, (size_t)J.nb * sizeof(BlockDesc), st));
+  launch_lz4block_fill(d_src, J.src_off, J.src_len, J.n, J.nblk, J.dst_off, J.olen, dst_cap, J.status, desc, st,
+                       launches);
+  CU(cudaEventRecord(S.ev_t0, st));
+  launch_lz4_decompress(desc, (uint32_t)J.nb, d_src, d_dst, J.status, J.counter, st, launches);
+  CU(cudaEventRecord(S.ev_t1, st));
+  launch_xxh32_verify(desc, (uint32_t)J.nb, d_dst, kXxhSeed, 0x0FFFFFFFu, J.status, st, launches);
+  CU(cudaEventRecord(S.ev_k1, st));
+  CU(cudaMemcpyAsync(J.h_down, J.d_down, J.down_bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(S.ev_b, st));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int get_device(uint32_t dev_index, Device** out) {
+  if (!g_ctx) return fail(B2S_E_NOT_INIT, "b2s_init has not been called%s");
+  if (dev_index >= g_ctx->devs.size()) return fail(B2S_E_ARG, "device index out of range%s");
+  *out = g_ctx->devs[dev_index];
+  CU(cudaSetDevice((*out)->ordinal));
+  return 0;
+}
+
+void add_timing(Slot& S, bool copies) {
+  t_timing.kernel_ms += ms_between(S.ev_k0, S.ev_k1);
+  t_timing.top_kernel_ms += ms_between(S.ev_t0, S.ev_t1);
+  if (copies) {
+    t_timing.h2d_ms += ms_between(S.ev_h0, S.ev_h1);
+    t_timing.d2h_ms += ms_between(S.ev_d0, S.ev_d1);
+  }
+}
+
+// groups streams [i0, i1) into chunks of ~kChunkBytes
+void make_chunks(uint32_t n, const uint64_t* len, std::vector<uint32_t>& starts) {
+  starts.clear();
+  uint32_t i = 0;
+  while (i < n) {
+    starts.push_back(i);
+    uint64_t bytes = 0;
+    uint32_t cnt = 0;
+    while (i < n && cnt < kChunkStreams && (cnt == 0 || bytes + len[i] <= kChunkBytes)) {
+      bytes += len[i];
+      i++;
+      cnt++;
+    }
+  }
+  starts.push_back(n);
+}
+
+// device layout of a chunk's sources: runs that are contiguous in host memory stay contiguous (one memcpy each)
+struct Run {
+  const uint8_t* host;
+  uint64_t dev_off;
+  uint64_t bytes;
+};
+uint64_t plan_runs(uint32_t cnt, const uint8_t* const* ptr, const uint64_t* len, uint64_t* dev_off,
+                   std::vector<Run>& runs) {
+  runs.clear();
+  uint64_t cur = 0;
+  for (uint32_t i = 0; i < cnt; i++) {
+    if (len[i] == 0) {
+      dev_off[i] = cur;
+      continue;
+    }
+    if (!runs.empty() && runs.back().host + runs.back().bytes == ptr[i]) {
+      dev_off[i] = runs.back().dev_off + runs.back().bytes;
+      runs.back().bytes += len[i];
+    } else {
+      // keep the host pointer's 16-byte phase so aligned fast paths behave the same as in host memory
+      cur = align_up(cur, 16) + ((uintptr_t)ptr[i] & 15u);
+      dev_off[i] = cur;
+      runs.push_back(Run{ptr[i], cur, len[i]});
+    }
+    cur = dev_off[i] + len[i];
+  }
+  return cur;
+}
+
+}  // namespace
+
+// ==============================================================================================================
+// C ABI
+// ==============================================================================================================
+extern "C" {
+
+uint32_t b2s_version(void) { return B2S_VERSION; }
+
+const char* b2s_strerror(int32_t code) {
+  switch (code) {
+    case B2S_OK: return "ok";
+    case B2S_E_CORRUPT: return "Stream is corrupted";
+    case B2S_E_CHECKSUM: return "Invalid checksum detected";
+    case B2S_E_DST_TOO_SMALL: return "destination too small";
+    case B2S_E_UNSUPPORTED: return "unsupported codec, checksum algorithm or parameter";
+    case B2S_E_ARG: return "invalid argument";
+    case B2S_E_CUDA: return "CUDA failure or no usable device";
+    case B2S_E_NOT_INIT: return "b2s_init has not been called";
+    case B2S_E_NOMEM: return "out of memory";
+    default: return "unknown error";
+  }
+}
+const char* b2s_last_error(void) { return t_last_error.c_str(); }
+
+int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_per_gpu) {
+  (void)pinned_bytes_per_gpu;
+  (void)streams_per_gpu;
+  std::lock_guard<std::mutex> lk(g_init_mtx);
+  if (g_ctx) return 0;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(B2S_E_CUDA, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  g_lz4_tile = env_int("B2S_LZ4_TILE", g_lz4_tile);
+  g_lz4_hlog = env_int("B2S_LZ4_HLOG", g_lz4_hlog);
+  g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
+  Context* C = new Context();
+  for (int d = 0; d < count && d < 32; d++) {
+    if (gpu_mask && !(gpu_mask & (1u << d))) continue;
+    CU(cudaSetDevice(d));
+    Device* D = new Device();
+    D->ordinal = d;
+    for (int k = 0; k < NSLOT; k++) {
+      Slot& S = D->slot[k];
+      CU(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+      cudaEvent_t* evs[] = {&S.ev_a, &S.ev_b, &S.ev_k0, &S.ev_k1, &S.ev_t0, &S.ev_t1, &S.ev_h0, &S.ev_h1, &S.ev_d0, &S.ev_d1};
+      for (auto p : evs) CU(cudaEventCreate(p));
+    }
+    if (checksum_tables_create(&D->tabs)) return fail(B2S_E_CUDA, "checksum table upload failed%s");
+    C->devs.push_back(D);
+  }
+  if (C->devs.empty()) {
+    delete C;
+    return fail(B2S_E_ARG, "gpu_mask selects no visible device%s");
+  }
+  g_ctx = C;
+  return 0;
+}
+
+void b2s_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_init_mtx);
+  if (!g_ctx) return;
+  for (Device* D : g_ctx->devs) {
+    cudaSetDevice(D->ordinal);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < NSLOT; k++) {
+      Slot& S = D->slot[k];
+      S.meta.release();
+      S.scratch.release();
+      S.desc.release();
+      S.src.release();
+      S.dst.release();
+      S.hmeta.release();
+      cudaEvent_t evs[] = {S.ev_a, S.ev_b, S.ev_k0, S.ev_k1, S.ev_t0, S.ev_t1, S.ev_h0, S.ev_h1, S.ev_d0, S.ev_d1};
+      for (auto ev : evs)
+        if (ev) cudaEventDestroy(ev);
+      if (S.st) cudaStreamDestroy(S.st);
+    }
+    checksum_tables_destroy(&D->tabs);
+    delete D;
+  }
+  delete g_ctx;
+  g_ctx = nullptr;
+}
+
+int b2s_device_count(void) { return g_ctx ? (int)g_ctx->devs.size() : B2S_E_NOT_INIT; }
+
+void* b2s_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    fail(B2S_E_NOMEM, "cudaHostAlloc failed%s");
+    return nullptr;
+  }
+  return p;
+}
+void b2s_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+int b2s_host_register(void* p, uint64_t bytes) {
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int b2s_host_unregister(void* p) {
+  CU(cudaHostUnregister(p));
+  return 0;
+}
+
+uint64_t b2s_compress_bound(uint32_t codec, uint32_t codec_block_size, uint64_t src_len) {
+  const uint64_t bs = block_size_or_default(codec, codec_block_size);
+  const uint64_t nb = (src_len + bs - 1) / bs;
+  switch (codec) {
+    case B2S_CODEC_LZ4BLOCK: return src_len + (nb + 1) * 21;  // RAW fallback bounds every block by its input
+    case B2S_CODEC_SNAPPY_XERIAL: return 16 + nb * (4 + 32 + bs + bs / 6);
+    case B2S_CODEC_ZSTD: return src_len + (src_len >> 8) + 64 + nb * 32;
+    default: return src_len;
+  }
+}
+
+void* b2s_dev_alloc(uint32_t dev_index, uint64_t bytes) {
+  Device* D;
+  if (get_device(dev_index, &D)) return nullptr;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    fail(B2S_E_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+void b2s_dev_free(uint32_t dev_index, void* p) {
+  Device* D;
+  if (get_device(dev_index, &D)) return;
+  if (p) cudaFree(p);
+}
+int b2s_dev_memcpy(uint32_t dev_index, void* dst, const void* src, uint64_t bytes, int kind) {
+  Device* D;
+  int rc = get_device(dev_index, &D);
+  if (rc) return rc;
+  cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  CU(cudaMemcpy(dst, src, bytes, k));
+  return 0;
+}
+
+int b2s_last_timing(b2s_timing* out) {
+  if (!out) return B2S_E_ARG;
+  *out = t_timing;
+  return 0;
+}
+uint64_t b2s_total_kernel_launches(void) { return g_ctx ? g_ctx->launches.load() : 0; }
+
+int b2s_gen_terasort_dev(uint32_t dev_index, void* d_dst, uint64_t first_record, uint64_t n_records, uint64_t seed) {
+  Device* D;
+  int rc = get_device(dev_index, &D);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(D->mtx);
+  launch_gen_terasort((uint8_t*)d_dst, first_record, n_records, seed, D->slot[0].st);
+  CU(cudaStreamSynchronize(D->slot[0].st));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// checksums
+// ------------------------------------------------------------------------------------------------------------
+static int checksum_chunk_dev(Device* D, Slot& S, uint32_t alg, uint32_t n, const uint8_t* d_base, const uint64_t* off,
+                              const uint64_t* len, uint64_t* out, uint64_t total_bytes, uint64_t* launches) {
+  if (alg < B2S_CHECKSUM_ADLER32 || alg > B2S_CHECKSUM_CRC32C)
+    return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
+  size_t up = align_up((size_t)n * 8, 16) * 2, down = align_up((size_t)n * 8, 16);
+  int rc = S.hmeta.ensure(up + down + 64);
+  if (rc) return rc;
+  size_t ws_elems = checksum_ws_elems(n) + 4;
+  rc = S.meta.ensure(up + down + align_up(((size_t)n + 1) * 8, 16) + ws_elems * 8 + 128);
+  if (rc) return rc;
+  Carver hc(S.hmeta.p), dc(S.meta.p);
+  uint64_t* h_off = hc.take<uint64_t>(n);
+  uint64_t* h_len = hc.take<uint64_t>(n);
+  hc.off = align_up(hc.off, 16);
+  uint64_t* h_out = hc.take<uint64_t>(n);
+  uint64_t* d_off = dc.take<uint64_t>(n);
+  uint64_t* d_len = dc.take<uint64_t>(n);
+  dc.off = align_up(dc.off, 16);
+  uint64_t* d_out = dc.take<uint64_t>(n);
+  uint64_t* d_work = dc.take<uint64_t>((size_t)n + 1);
+  uint64_t* d_ws = dc.take<uint64_t>(ws_elems);
+  memcpy(h_off, off, (size_t)n * 8);
+  memcpy(h_len, len, (size_t)n * 8);
+  cudaStream_t st = S.st;
+  CU(cudaMemcpyAsync(d_off, h_off, up, cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(S.ev_k0, st));
+  CU(cudaEventRecord(S.ev_t0, st));
+  launch_checksum(D->tabs, alg, d_base, d_off, d_len, n, pick_tile_shift(total_bytes), d_work, d_ws, d_out, st,
+                  launches);
+  CU(cudaEventRecord(S.ev_t1, st));
+  CU(cudaEventRecord(S.ev_k1, st));
+  CU(cudaMemcpyAsync(h_out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  memcpy(out, h_out, (size_t)n * 8);
+  return 0;
+}
+
+int b2s_checksum_dev(uint32_t dev_index, uint32_t alg, uint32_t n, const void* d_base, const uint64_t* off,
+                     const uint64_t* len, uint64_t* out) {
+  WallTimer wt;
+  t_timing = b2s_timing{};
+  Device* D;
+  int rc = get_device(dev_index, &D);
+  if (rc) return rc;
+  if (!n) return 0;
+  std::lock_guard<std::mutex> lk(D->mtx);
+  uint64_t total = 0, launches = 0;
+  for (uint32_t i = 0; i < n; i++) total += len[i];
+  rc = checksum_chunk_dev(D, D->slot[0], alg, n, (const uint8_t*)d_base, off, len, out, total, &launches);
+  if (rc) return rc;
+  add_timing(D->slot[0], false);
+  t_timing.kernel_launches = launches;
+  t_timing.src_bytes = total;
+  t_timing.total_ms = wt.ms();
+  g_ctx->launches += launches;
+  return 0;
+}
+
+static int checksum_host(uint32_t alg, uint32_t n, const uint8_t* const* ptr, const uint64_t* len, uint64_t* out) {
+  WallTimer wt;
+  t_timing = b2s_timing{};
+  Device* D;
+  int rc = get_device(0, &D);
+  if (rc) return rc;
+  if (!n) return 0;
+  std::lock_guard<std::mutex> lk(D->mtx);
+  std::vector<uint32_t> starts;
+  make_chunks(n, len, starts);
+  std::vector<uint64_t> dev_off;
+  std::vector<Run> runs;
+  uint64_t launches = 0;
+  for (size_t c = 0; c + 1 < starts.size(); c++) {
+    Slot& S = D->slot[0];
+    const uint32_t i0 = starts[c], cnt = starts[c + 1] - starts[c];
+    dev_off.resize(cnt);
+    uint64_t bytes = plan_runs(cnt, ptr + i0, len + i0, dev_off.data(), runs);
+    rc = S.src.ensure(bytes + 64);
+    if (rc) return rc;
+    CU(cudaEventRecord(S.ev_h0, S.st));
+    for (const Run& r : runs)
+      CU(cudaMemcpyAsync((uint8_t*)S.src.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, S.st));
+    CU(cudaEventRecord(S.ev_h1, S.st));
+    rc = checksum_chunk_dev(D, S, alg, cnt, (const uint8_t*)S.src.p, dev_off.data(), len + i0, out + i0, bytes,
+                            &launches);
+    if (rc) return rc;
+    add_timing(S, false);
+    t_timing.h2d_ms += ms_between(S.ev_h0, S.ev_h1);
+    t_timing.h2d_bytes += bytes;
+    t_timing.d2h_bytes += (uint64_t)cnt * 8;
+    t_timing.src_bytes += bytes;
+  }
+  t_timing.kernel_launches = launches;
+  t_timing.total_ms = wt.ms();
+  g_ctx->launches += launches;
+  return 0;
+}
+
+int b2s_checksum_batch(uint32_t alg, uint32_t n, const uint8_t* const* src, const uint64_t* len, uint64_t* out) {
+  if (n && (!src || !len || !out)) return fail(B2S_E_ARG, "null argument%s");
+  return checksum_host(alg, n, src, len, out);
+}
+int b2s_checksum_packed(uint32_t alg, uint32_t n, const uint8_t* base, const uint64_t* off, const uint64_t* len,
+                        uint64_t* out) {
+  if (n && (!base || !off || !len || !out)) return fail(B2S_E_ARG, "null argument%s");
+  std::vector<const uint8_t*> ptr(n);
+  for (uint32_t i = 0; i < n; i++) ptr[i] = base + off[i];
+  return checksum_host(alg, n, ptr.data(), len, out);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// write side
+// ------------------------------------------------------------------------------------------------------------
+int b2s_compress_dev(uint32_t dev_index, uint32_t codec, int32_t level, uint32_t codec_block_size,
+                     uint32_t checksum_alg, uint32_t n, const void* d_src_base, const uint64_t* src_off,
+                     const uint64_t* src_len, void* d_dst_base, uint64_t dst_cap, uint64_t* dst_off,
+                     uint64_t* dst_len, uint64_t* dst_total, uint64_t* checksum_out, int32_t* status) {
+  (void)level;
+  WallTimer wt;
+  t_timing = b2s_timing{};
+  Device* D;
+  int rc = get_device(dev_index, &D);
+  if (rc) return rc;
+  if (checksum_alg > B2S_CHECKSUM_CRC32C) return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
+  if (dst_total) *dst_total = 0;
+  if (!n) return 0;
+  if (!src_off || !src_len || !dst_off || !dst_len || !status) return fail(B2S_E_ARG, "null argument%s");
+  std::lock_guard<std::mutex> lk(D->mtx);
+  Slot& S = D->slot[0];
+  const uint32_t bs = block_size_or_default(codec, codec_block_size);
+  CompressJob J;
+  rc = compress_prepare(S, codec, bs, n, src_len, J);
+  if (rc) return rc;
+  memcpy(J.h_src_off, src_off, (size_t)n * 8);
+  memcpy(J.h_src_len, src_len, (size_t)n * 8);
+  CompressDevMeta M;
+  uint64_t launches = 0;
+  rc = compress_enqueue(g_ctx, S, D->tabs, bs, checksum_alg, J, (const uint8_t*)d_src_base, (uint8_t*)d_dst_base,
+                        dst_cap, M, &launches);
+  if (rc) return rc;
+  CU(cudaEventSynchronize(S.ev_a));
+  CU(cudaGetLastError());
+  memcpy(dst_off, J.h_dst_off, (size_t)n * 8);
+  memcpy(dst_len, J.h_dst_len, (size_t)n * 8);
+  memcpy(status, J.h_status, (size_t)n * 4);
+  if (checksum_out) {
+    if (checksum_alg) memcpy(checksum_out, J.h_cks, (size_t)n * 8);
+    else memset(checksum_out, 0, (size_t)n * 8);
+  }
+  uint64_t total = J.h_total[0] + 21ull * n, srcb = 0;
+  for (uint32_t i = 0; i < n; i++) srcb += src_len[i];
+  if (dst_total) *dst_total = total;
+  add_timing(S, false);
+  t_timing.kernel_launches = launches;
+  t_timing.src_bytes = srcb;
+  t_timing.dst_bytes = total;
+  t_timing.total_ms = wt.ms();
+  g_ctx->launches += launches;
+  return 0;
+}
+
+// shared engine for the host-pointer write path.  packed_dst != nullptr: outputs back to back into that arena.
+static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg, uint32_t n,
+                         const uint8_t* const* src, const uint64_t* src_len, uint8_t* packed_dst, uint64_t packed_cap,
+                         uint8_t* const* dst, const uint64_t* dst_cap, uint64_t* dst_off, uint64_t* dst_len,
+                         uint64_t* dst_total, uint64_t* checksum_out, int32_t* status) {
+  WallTimer wt;
+  t_timing = b2s_timing{};
+  Device* D;
+  int rc = get_device(0, &D);
+  if (rc) return rc;
+  if (alg > B2S_CHECKSUM_CRC32C) return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
+  if (dst_total) *dst_total = 0;
+  if (!n) return 0;
+  std::lock_guard<std::mutex> lk(D->mtx);
+  const uint32_t bs = block_size_or_default(codec, codec_block_size);
+  std::vector<uint32_t> starts;
+  make_chunks(n, src_len, starts);
+  const size_t nchunks = starts.size() - 1;
+  std::vector<CompressJob> jobs(nchunks);
+  std::vector<std::vector<Run>> runs(NSLOT);
+  uint64_t launches = 0, run_off = 0;
+
+  auto finish = [&](size_t c) -> int {
+    Slot& S = D->slot[c % NSLOT];
+    CompressJob& J = jobs[c];
+    const uint32_t i0 = starts[c];
+    CU(cudaEventSynchronize(S.ev_a));
+    add_timing(S, true);
+    const uint64_t chunk_total = J.h_total[0] + 21ull * J.n;
+    for (uint32_t k = 0; k < J.n; k++) {
+      status[i0 + k] = J.h_status[k];
+      dst_len[i0 + k] = J.h_dst_len[k];
+      if (checksum_out) checksum_out[i0 + k] = alg ? J.h_cks[k] : 0;
+    }
+    CU(cudaEventRecord(S.ev_d0, S.st));
+    if (packed_dst) {
+      if (run_off + chunk_total > packed_cap) {
+        for (uint32_t k = 0; k < J.n; k++) {
+          dst_off[i0 + k] = run_off + J.h_dst_off[k];
+          if (run_off + J.h_dst_off[k] + J.h_dst_len[k] > packed_cap) status[i0 + k] = B2S_E_DST_TOO_SMALL;
+        }
+        // copy what fits so that earlier streams of the chunk stay valid
+        uint64_t fit = packed_cap > run_off ? packed_cap - run_off : 0;
+        if (fit) CU(cudaMemcpyAsync(packed_dst + run_off, S.dst.p, fit, cudaMemcpyDeviceToHost, S.st));
+        t_timing.d2h_bytes += fit;
+      } else {
+        for (uint32_t k = 0; k < J.n; k++) dst_off[i0 + k] = run_off + J.h_dst_off[k];
+        if (chunk_total) CU(cudaMemcpyAsync(packed_dst + run_off, S.dst.p, chunk_total, cudaMemcpyDeviceToHost, S.st));
+        t_timing.d2h_bytes += chunk_total;
+      }
+      run_off += chunk_total;
+    } else {
+      for (uint32_t k = 0; k < J.n; k++) {
+        const uint32_t i = i0 + k;
+        if (status[i] != 0) continue;
+        if (J.h_dst_len[k] > dst_cap[i]) {
+          status[i] = B2S_E_DST_TOO_SMALL;
+          continue;
+        }
+        CU(cudaMemcpyAsync(dst[i], (uint8_t*)S.dst.p + J.h_dst_off[k], J.h_dst_len[k], cudaMemcpyDeviceToHost, S.st));
+        t_timing.d2h_bytes += J.h_dst_len[k];
+      }
+      run_off += chunk_total;
+    }
+    CU(cudaEventRecord(S.ev_d1, S.st));
+    t_timing.dst_bytes += chunk_total;
+    return 0;
+  };
+
+  for (size_t c = 0; c < nchunks; c++) {
+    Slot& S = D->slot[c % NSLOT];
+    if (c >= NSLOT) {
+      rc = finish(c - NSLOT);
+      if (rc) return rc;
+      CU(cudaStreamSynchronize(S.st));  // payload of the slot's previous chunk has left the device
+      t_timing.d2h_ms += ms_between(S.ev_d0, S.ev_d1);
+    }
+    const uint32_t i0 = starts[c], cnt = starts[c + 1] - starts[c];
+    CompressJob& J = jobs[c];
+    rc = compress_prepare(S, codec, bs, cnt, src_len + i0, J);
+    if (rc) return rc;
+    memcpy(J.h_src_len, src_len + i0, (size_t)cnt * 8);
+    uint64_t bytes = plan_runs(cnt, src + i0, src_len + i0, J.h_src_off, runs[c % NSLOT]);
+    rc = S.src.ensure(bytes + 64);
+    if (rc) return rc;
+    uint64_t bound = 0;
+    for (uint32_t k = 0; k < cnt; k++) bound += b2s_compress_bound(codec, bs, src_len[i0 + k]);
+    rc = S.dst.ensure(bound + 64);
+    if (rc) return rc;
+    CU(cudaEventRecord(S.ev_h0, S.st));
+    for (const Run& r : runs[c % NSLOT])
+      CU(cudaMemcpyAsync((uint8_t*)S.src.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, S.st));
+    CU(cudaEventRecord(S.ev_h1, S.st));
+    t_timing.h2d_bytes += bytes;
+    t_timing.src_bytes += bytes;
+    CompressDevMeta M;
+    rc = compress_enqueue(g_ctx, S, D->tabs, bs, alg, J, (const uint8_t*)S.src.p, (uint8_t*)S.dst.p, S.dst.cap, M,
+                          &launches);
+    if (rc) return rc;
+  }
+  for (size_t c = nchunks > NSLOT ? nchunks - NSLOT : 0; c < nchunks; c++) {
+    rc = finish(c);
+    if (rc) return rc;
+  }
+  for (int k = 0; k < NSLOT; k++) {
+    CU(cudaStreamSynchronize(D->slot[k].st));
+    if ((size_t)k < nchunks) t_timing.d2h_ms += ms_between(D->slot[k].ev_d0, D->slot[k].ev_d1);
+  }
+  CU(cudaGetLastError());
+  if (dst_total) *dst_total = run_off;
+  t_timing.kernel_launches = launches;
+  t_timing.total_ms = wt.ms();
+  g_ctx->launches += launches;
+  return 0;
+}
+
+int b2s_compress_batch(uint32_t codec, int32_t level, uint32_t codec_block_size, uint32_t checksum_alg, uint32_t n,
+                       const uint8_t* const* src, const uint64_t* src_len, uint8_t* const* dst,
+                       const uint64_t* dst_cap, uint64_t* dst_len, uint64_t* checksum_out, int32_t* status) {
+  (void)level;
+  if (n && (!src || !src_len || !dst || !dst_cap || !dst_len || !status)) return fail(B2S_E_ARG, "null argument%s");
+  std::vector<uint64_t> off(n);
+  return compress_host(codec, codec_block_size, checksum_alg, n, src, src_len, nullptr, 0, dst, dst_cap, off.data(),
+                       dst_len, nullptr, checksum_out, status);
+}
+
+int b2s_compress_packed(uint32_t codec, int32_t level, uint32_t codec_block_size, uint32_t checksum_alg, uint32_t n,
+                        const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
+                        uint64_t dst_cap, uint64_t* dst_off, uint64_t* dst_len, uint64_t* dst_total,
+                        uint64_t* checksum_out, int32_t* status) {
+  (void)level;
+  if (n && (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_len || !status))
+    return fail(B2S_E_ARG, "null argument%s");
+  std::vector<const uint8_t*> ptr(n);
+  for (uint32_t i = 0; i < n; i++) ptr[i] = src_base + src_off[i];
+  return compress_host(codec, codec_block_size, checksum_alg, n, ptr.data(), src_len, dst_base, dst_cap, nullptr,
+                       nullptr, dst_off, dst_len, dst_total, checksum_out, status);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// read side
+// ------------------------------------------------------------------------------------------------------------
+// fills the slice arrays of a job for blocks [i0, i0+cnt); dev_off = device offsets of the blocks
+static void fill_slices(DecompressJob& J, uint32_t i0, uint32_t cnt, const uint64_t* dev_off, const uint64_t* src_len,
+                        const uint32_t* slice_base, const uint64_t* slice_len, const uint64_t* slice_sum) {
+  uint32_t s = 0;
+  for (uint32_t k = 0; k < cnt; k++) {
+    J.h_slice_base[k] = s;
+    if (!J.n_slices) continue;
+    uint64_t o = dev_off[k];
+    for (uint32_t q = slice_base[i0 + k]; q < slice_base[i0 + k + 1]; q++) {
+      J.h_slice_off[s] = o;
+      J.h_slice_len[s] = slice_len[q];
+      J.h_slice_sum[s] = slice_sum[q];
+      J.h_slice_owner[s] = k;
+      o += slice_len[q];
+      s++;
+    }
+    (void)src_len;
+  }
+  J.h_slice_base[cnt] = s;
+}
+
+// slices of a block must tile it exactly (S3ChecksumValidationStream walks .index differences over the block)
+static int check_slices(uint32_t n, const uint64_t* src_len, const uint32_t* slice_base, const uint64_t* slice_len) {
+  for (uint32_t i = 0; i < n; i++) {
+    uint64_t sum = 0;
+    if (slice_base[i + 1] < slice_base[i]) return fail(B2S_E_ARG, "slice_base must be non-decreasing%s");
+    for (uint32_t q = slice_base[i]; q < slice_base[i + 1]; q++) sum += slice_len[q];
+    if (sum != src_len[i]) return fail(B2S_E_ARG, "slice lengths of a block must sum to its length%s");
+  }
+  return 0;
+}
+
+int b2s_decompress_dev(uint32_t dev_index, uint32_t codec, uint32_t checksum_alg, uint32_t n, const void* d_src_base,
+                       const uint64_t* src_off, const uint64_t* src_len, const uint32_t* slice_base,
+                       const uint64_t* slice_len, const uint64_t* slice_checksum, void* d_dst_base, uint64_t dst_cap,
+                       uint64_t* dst_off, uint64_t* dst_len, uint64_t* dst_total, int32_t* status,
+                       int32_t* bad_slice) {
+  WallTimer wt;
+  t_timing = b2s_timing{};
+  Device* D;
+  int rc = get_device(dev_index, &D);
+  if (rc) return rc;
+  if (checksum_alg > B2S_CHECKSUM_CRC32C) return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
+  if (dst_total) *dst_total = 0;
+  if (!n) return 0;
+  if (!src_off || !src_len || !dst_off || !dst_len || !status) return fail(B2S_E_ARG, "null argument%s");
+  if (checksum_alg && (!slice_base || !slice_len || !slice_checksum)) return fail(B2S_E_ARG, "slice arrays required%s");
+  if (checksum_alg && (rc = check_slices(n, src_len, slice_base, slice_len))) return rc;
+  std::lock_guard<std::mutex> lk(D->mtx);
+  Slot& S = D->slot[0];
+  DecompressJob J;
+  const uint32_t ns = checksum_alg ? slice_base[n] : 0;
+  rc = decompress_prepare(S, codec, checksum_alg, n, ns, J);
+  if (rc) return rc;
+  memcpy(J.h_src_off, src_off, (size_t)n * 8);
+  memcpy(J.h_src_len, src_len, (size_t)n * 8);
+  fill_slices(J, 0, n, src_off, src_len, slice_base, slice_len, slice_checksum);
+  uint64_t srcb = 0, launches = 0;
+  for (uint32_t i = 0; i < n; i++) srcb += src_len[i];
+  rc = decompress_enqueue_a(S, D->tabs, checksum_alg, J, (const uint8_t*)d_src_base, srcb, &launches);
+  if (rc) return rc;
+  CU(cudaEventSynchronize(S.ev_a));
+  rc = decompress_enqueue_b(S, J, (const uint8_t*)d_src_base, (uint8_t*)d_dst_base, dst_cap, &launches);
+  if (rc) return rc;
+  CU(cudaEventSynchronize(S.ev_b));
+  CU(cudaGetLastError());
+  memcpy(dst_off, J.h_dst_off, (size_t)n * 8);
+  memcpy(dst_len, J.h_dst_len, (size_t)n * 8);
+  memcpy(status, J.h_status, (size_t)n * 4);
+  if (bad_slice) memcpy(bad_slice, J.h_bad, (size_t)n * 4);
+  if (dst_total) *dst_total = J.total_out;
+  add_timing(S, false);
+  t_timing.kernel_launches = launches;
+  t_timing.src_bytes = srcb;
+  t_timing.dst_bytes = J.total_out;
+  t_timing.total_ms = wt.ms();
+  g_ctx->launches += launches;
+  return 0;
+}
+
+static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8_t* const* src,
+                           const uint64_t* src_len, const uint32_t* slice_base, const uint64_t* slice_len,
+                           const uint64_t* slice_sum, uint8_t* packed_dst, uint64_t packed_cap, uint8_t* const* dst,
+                           const uint64_t* dst_cap, uint64_t* dst_off, uint64_t* dst_len, uint64_t* dst_total,
+                           int32_t* status, int32_t* bad_slice, bool size_only) {
+  WallTimer wt;
+  t_timing = b2s_timing{};
+  Device* D;
+  int rc = get_device(0, &D);
+  if (rc) return rc;
+  if (alg > B2S_CHECKSUM_CRC32C) return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
+  if (dst_total) *dst_total = 0;
+  if (!n) return 0;
+  if (alg && (rc = check_slices(n, src_len, slice_base, slice_len))) return rc;
+  std::lock_guard<std::mutex> lk(D->mtx);
+  std::vector<uint32_t> starts;
+  make_chunks(n, src_len, starts);
+  const size_t nchunks = starts.size() - 1;
+  std::vector<DecompressJob> jobs(nchunks);
+  std::vector<uint64_t> chunk_src_bytes(nchunks);
+  std::vector<std::vector<Run>> runs(NSLOT);
+  uint64_t launches = 0, run_off = 0;
+
+  auto stage_a = [&](size_t c) -> int {
+    Slot& S = D->slot[c % NSLOT];
+    if (c >= NSLOT) {
+      CU(cudaStreamSynchronize(S.st));
+      t_timing.d2h_ms += ms_between(S.ev_d0, S.ev_d1);
+    }
+    const uint32_t i0 = starts[c], cnt = starts[c + 1] - starts[c];
+    DecompressJob& J = jobs[c];
+    const uint32_t ns = alg ? slice_base[i0 + cnt] - slice_base[i0] : 0;
+    int r = decompress_prepare(S, codec, alg, cnt, ns, J);
+    if (r) return r;
+    memcpy(J.h_src_len, src_len + i0, (size_t)cnt * 8);
+    uint64_t bytes = plan_runs(cnt, src + i0, src_len + i0, J.h_src_off, runs[c % NSLOT]);
+    chunk_src_bytes[c] = bytes;
+    fill_slices(J, i0, cnt, J.h_src_off, src_len, slice_base, slice_len, slice_sum);
+    r = S.src.ensure(bytes + 64);
+    if (r) return r;
+    CU(cudaEventRecord(S.ev_h0, S.st));
+    for (const Run& q : runs[c % NSLOT])
+      CU(cudaMemcpyAsync((uint8_t*)S.src.p + q.dev_off, q.host, q.bytes, cudaMemcpyHostToDevice, S.st));
+    CU(cudaEventRecord(S.ev_h1, S.st));
+    t_timing.h2d_bytes += bytes;
+    t_timing.src_bytes += bytes;
+    return decompress_enqueue_a(S, D->tabs, alg, J, (const uint8_t*)S.src.p, bytes, &launches);
+  };
+  auto stage_b = [&](size_t c) -> int {
+    Slot& S = D->slot[c % NSLOT];
+    DecompressJob& J = jobs[c];
+    CU(cudaEventSynchronize(S.ev_a));
+    if (size_only) {
+      J.total_out = J.h_totals[1];
+      CU(cudaMemcpyAsync(J.h_down, J.d_down, J.down_bytes, cudaMemcpyDeviceToHost, S.st));
+      CU(cudaEventRecord(S.ev_b, S.st));
+      return 0;
+    }
+    int r = S.dst.ensure(J.h_totals[1] + 64);
+    if (r) return r;
+    return decompress_enqueue_b(S, J, (const uint8_t*)S.src.p, (uint8_t*)S.dst.p, S.dst.cap, &launches);
+  };
+  auto stage_c = [&](size_t c) -> int {
+    Slot& S = D->slot[c % NSLOT];
+    DecompressJob& J = jobs[c];
+    const uint32_t i0 = starts[c];
+    CU(cudaEventSynchronize(S.ev_b));
+    if (!size_only) add_timing(S, true);
+    CU(cudaEventRecord(S.ev_d0, S.st));
+    for (uint32_t k = 0; k < J.n; k++) {
+      const uint32_t i = i0 + k;
+      status[i] = J.h_status[k];
+      dst_len[i] = size_only ? J.h_dst_len[k] : J.h_dst_len[k];
+      if (bad_slice) bad_slice[i] = J.h_bad[k];
+      if (dst_off) dst_off[i] = run_off + J.h_dst_off[k];
+    }
+    if (size_only) {
+      // h_dst_len holds olen from phase A
+    } else if (packed_dst) {
+      uint64_t fit = J.total_out;
+      if (run_off + J.total_out > packed_cap) {
+        fit = packed_cap > run_off ? packed_cap - run_off : 0;
+        for (uint32_t k = 0; k < J.n; k++)
+          if (status[i0 + k] == 0 && run_off + J.h_dst_off[k] + J.h_dst_len[k] > packed_cap)
+            status[i0 + k] = B2S_E_DST_TOO_SMALL;
+      }
+      if (fit) CU(cudaMemcpyAsync(packed_dst + run_off, S.dst.p, fit, cudaMemcpyDeviceToHost, S.st));
+      t_timing.d2h_bytes += fit;
+    } else {
+      for (uint32_t k = 0; k < J.n; k++) {
+        const uint32_t i = i0 + k;
+        if (status[i] != 0 || J.h_dst_len[k] == 0) continue;
+        if (J.h_dst_len[k] > dst_cap[i]) {
+          status[i] = B2S_E_DST_TOO_SMALL;
+          continue;
+        }
+        CU(cudaMemcpyAsync(dst[i], (uint8_t*)S.dst.p + J.h_dst_off[k], J.h_dst_len[k], cudaMemcpyDeviceToHost, S.st));
+        t_timing.d2h_bytes += J.h_dst_len[k];
+      }
+    }
+    CU(cudaEventRecord(S.ev_d1, S.st));
+    run_off += J.total_out;
+    t_timing.dst_bytes += J.total_out;
+    return 0;
+  };
+
+  for (size_t c = 0; c < nchunks + 2; c++) {
+    if (c >= 2 && c - 2 < nchunks && (rc = stage_c(c - 2))) return rc;
+    if (c < nchunks && (rc = stage_a(c))) return rc;
+    if (c >= 1 && c - 1 < nchunks && (rc = stage_b(c - 1))) return rc;
+  }
+  for (int k = 0; k < NSLOT; k++) {
+    CU(cudaStreamSynchronize(D->slot[k].st));
+    if ((size_t)k < nchunks) t_timing.d2h_ms += ms_between(D->slot[k].ev_d0, D->slot[k].ev_d1);
+  }
+  CU(cudaGetLastError());
+  if (dst_total) *dst_total = run_off;
+  t_timing.kernel_launches = launches;
+  t_timing.total_ms = wt.ms();
+  g_ctx->launches += launches;
+  return 0;
+}
+
+// builds the flattened slice arrays used by the engine from the per-block pointer form
+static int flatten_slices(uint32_t n, const uint32_t* n_slices, const uint64_t* const* slice_len,
+                          const uint64_t* const* slice_checksum, std::vector<uint32_t>& base,
+                          std::vector<uint64_t>& len, std::vector<uint64_t>& sum) {
+  base.assign((size_t)n + 1, 0);
+  for (uint32_t i = 0; i < n; i++) base[i + 1] = base[i] + n_slices[i];
+  len.resize(base[n]);
+  sum.resize(base[n]);
+  for (uint32_t i = 0; i < n; i++)
+    for (uint32_t k = 0; k < n_slices[i]; k++) {
+      len[base[i] + k] = slice_len[i][k];
+      sum[base[i] + k] = slice_checksum[i][k];
+    }
+  return 0;
+}
+
+int b2s_decompress_batch(uint32_t codec, uint32_t checksum_alg, uint32_t n, const uint8_t* const* src,
+                         const uint64_t* src_len, const uint32_t* n_slices, const uint64_t* const* slice_len,
+                         const uint64_t* const* slice_checksum, uint8_t* const* dst, const uint64_t* dst_cap,
+                         uint64_t* dst_len, int32_t* status, int32_t* bad_slice) {
+  if (n && (!src || !src_len || !dst || !dst_cap || !dst_len || !status)) return fail(B2S_E_ARG, "null argument%s");
+  if (checksum_alg && n && (!n_slices || !slice_len || !slice_checksum)) return fail(B2S_E_ARG, "slice arrays required%s");
+  std::vector<uint32_t> base;
+  std::vector<uint64_t> len, sum;
+  if (checksum_alg) flatten_slices(n, n_slices, slice_len, slice_checksum, base, len, sum);
+  return decompress_host(codec, checksum_alg, n, src, src_len, base.data(), len.data(), sum.data(), nullptr, 0, dst,
+                         dst_cap, nullptr, dst_len, nullptr, status, bad_slice, false);
+}
+
+int b2s_decompress_packed(uint32_t codec, uint32_t checksum_alg, uint32_t n, const uint8_t* src_base,
+                          const uint64_t* src_off, const uint64_t* src_len, const uint32_t* slice_base,
+                          const uint64_t* slice_len, const uint64_t* slice_checksum, uint8_t* dst_base,
+                          uint64_t dst_cap, uint64_t* dst_off, uint64_t* dst_len, uint64_t* dst_total,
+                          int32_t* status, int32_t* bad_slice) {
+  if (n && (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_len || !status))
+    return fail(B2S_E_ARG, "null argument%s");
+  if (checksum_alg && n && (!slice_base || !slice_len || !slice_checksum))
+    return fail(B2S_E_ARG, "slice arrays required%s");
+  std::vector<const uint8_t*> ptr(n);
+  for (uint32_t i = 0; i < n; i++) ptr[i] = src_base + src_off[i];
+  return decompress_host(codec, checksum_alg, n, ptr.data(), src_len, slice_base, slice_len, slice_checksum, dst_base,
+                         dst_cap, nullptr, nullptr, dst_off, dst_len, dst_total, status, bad_slice, false);
+}
+
+int b2s_decompressed_size_batch(uint32_t codec, uint32_t n, const uint8_t* const* src, const uint64_t* src_len,
+                                uint64_t* out_len, int32_t* status) {
+  if (n && (!src || !src_len || !out_len || !status)) return fail(B2S_E_ARG, "null argument%s");
+  return decompress_host(codec, 0, n, src, src_len, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                         out_len, nullptr, status, nullptr, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// kernels.h — internal launch interface between the C-ABI runtime (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b2s {
+
+// ---------------- scan.cu ----------------
+// in-place exclusive prefix sum over d_v[0..n); d_total (device, 1 element) receives the grand total.
+// d_ws must hold scan_ws_elems(n) uint64.
+size_t scan_ws_elems(size_t n);
+void launch_exclusive_scan_u64(uint64_t* d_v, size_t n, uint64_t* d_total, uint64_t* d_ws, cudaStream_t st,
+                               uint64_t* launches);
+
+// ---------------- checksum.cu (K1) ----------------
+struct ChecksumTables {
+  uint32_t* d_crc_rows[2];  // [crc32, crc32c] : 16 x 256 row-advance tables (Z_496..Z_511)
+  uint32_t* d_crc_misc[2];  // x2n[32] | xinv2n[32] | lane_const[32] | poly
+};
+int checksum_tables_create(ChecksumTables* t);  // on the current device
+void checksum_tables_destroy(ChecksumTables* t);
+inline size_t checksum_ws_elems(size_t n) { return scan_ws_elems(n + 1) + 2 * n + 2; }
+// slices i = [d_off[i], d_off[i]+d_len[i]) of base; d_out[i] = checksum (low 32 bits).  tile_shift: log2 bytes per
+// warp work item (>= 9).  d_work_base[n+1] is scratch for the work-item prefix; d_ws >= checksum_ws_elems(n).
+void launch_checksum(const ChecksumTables& t, uint32_t alg, const uint8_t* base, const uint64_t* d_off,
+                     const uint64_t* d_len, uint32_t n, uint32_t tile_shift, uint64_t* d_work_base, uint64_t* d_ws,
+                     uint64_t* d_out, cudaStream_t st, uint64_t* launches);
+// verify: slice s of block owner[s] mismatching -> status[owner]=B2S_E_CHECKSUM, bad_slice[owner]=min(s-slice_base[owner])
+void launch_checksum_compare(const uint64_t* d_got, const uint64_t* d_expected, const uint32_t* d_slice_owner,
+                             const uint32_t* d_slice_base, uint32_t n_slices, int32_t* d_status, int32_t* d_bad_slice,
+                             cudaStream_t st, uint64_t* launches);
+
+// ---------------- xxh32.cu (K2) ----------------
+void launch_xxh32_encode(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                         const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
+                         uint32_t seed, uint32_t* d_hash, cudaStream_t st, uint64_t* launches);
+void launch_xxh32_verify(const BlockDesc* d_desc, uint32_t n_blocks, const uint8_t* dst_base, uint32_t seed,
+                         uint32_t mask, int32_t* d_status, cudaStream_t st, uint64_t* launches);
+
+// ---------------- lz4.cu (K3/K4 + LZ4Block framing) ----------------
+extern int g_lz4_tile, g_lz4_hlog, g_lz4d_tile;
+// compress every codec block into scratch (stride block_size); csize[b] = payload bytes (bit 31 = stored RAW);
+// sizes[b] = 21 + payload (input of the packing scan)
+void launch_lz4_compress(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                         const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
+                         uint8_t* d_scratch, uint32_t* d_csize, uint64_t* d_sizes, unsigned int* d_counter,
+                         cudaStream_t st, uint64_t* launches);
+// headers + payloads + end marks at their packed offsets (d_scan = exclusive scan of sizes); fills dst_off/dst_len
+void launch_lz4block_pack(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                          const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
+                          const uint8_t* d_scratch, const uint32_t* d_csize, const uint32_t* d_hash,
+                          const uint64_t* d_scan, const uint64_t* d_scan_total, uint8_t* dst_base, uint64_t dst_cap,
+                          uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status, cudaStream_t st,
+                          uint64_t* launches);
+// header walk pass 1: per stream block count + decoded bytes; malformed -> status CORRUPT (streams already failed are skipped)
+void launch_lz4block_count(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
+                           uint64_t* d_nblk, uint64_t* d_olen, int32_t* d_status, cudaStream_t st,
+                           uint64_t* launches);
+// header walk pass 2: descriptors at d_blk_base[i]+k; streams that overflow dst_cap get status DST_TOO_SMALL + no-op descriptors
+void launch_lz4block_fill(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
+                          const uint64_t* d_blk_base, const uint64_t* d_dst_off, uint64_t* d_olen, uint64_t dst_cap,
+                          int32_t* d_status, BlockDesc* d_desc, cudaStream_t st, uint64_t* launches);
+void launch_lz4_decompress(const BlockDesc* d_desc, uint32_t n_blocks, const uint8_t* src_base, uint8_t* dst_base,
+                           int32_t* d_status, unsigned int* d_counter, cudaStream_t st, uint64_t* launches);
+
+// ---------------- gen.cu (bench utility) ----------------
+void launch_gen_terasort(uint8_t* d_dst, uint64_t first_record, uint64_t n_records, uint64_t seed, cudaStream_t st);
+
+}  // namespace b2s
