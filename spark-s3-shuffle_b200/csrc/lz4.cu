@@ -145,8 +145,18 @@ __global__ void __launch_bounds__(kLz4Threads) lz4_compress_kernel(
           next = pos + TILE;
         }
         tile_sync<TILE>();  // all lanes have read the table for this window
-        if (valid && p < next) table[h] = (uint16_t)p;  // slot conflicts: highest lane (latest position) wins
+        // insert the window's positions that precede the next scan position.  Two lanes may hash to one slot and the
+        // hardware's same-address store winner is unspecified, so losers with a *later* position re-store until the
+        // slot holds the highest position (= what a sequential scan would leave).  Usually one read-back, no retry.
+        const bool ins = valid && p < next;
+        if (ins) table[h] = (uint16_t)p;
         tile_sync<TILE>();
+        for (;;) {
+          const bool lost = ins && table[h] < (uint16_t)p;
+          if (!tile_ballot<TILE>(lost)) break;
+          if (lost) table[h] = (uint16_t)p;
+          tile_sync<TILE>();
+        }
         pos = next;
       }
     }
