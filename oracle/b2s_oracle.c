@@ -223,53 +223,59 @@ last_literals:
 }
 
 /*
- * CPU model of the GPU LZ4 compressor (spark-s3-shuffle_b200/csrc/lz4_compress.cu).
- * A tile of W lanes inspects W consecutive positions per step; the lowest lane with a verified 4-byte match
- * wins; the match is extended forward; positions of the window that lie before the next scan position are
- * inserted (highest position wins a hash-slot conflict).  u16 table, zero-initialised, so n <= 65536.
+ * CPU model of the GPU LZ4 compressor (spark-s3-shuffle_b200/csrc/lz4.cu) — its executable
+ * specification: the kernel's output is bit-identical.  "Window-batched greedy": the 32 positions of a window are
+ * looked up against the hash table as it stood before the window (so a match never references its own window
+ * through the table; byte runs are caught by an explicit offset-1 candidate instead), the parse then walks the window greedily (lowest matching position at or after the parse
+ * cursor, full forward extension), and finally every position of the window is inserted (highest position wins a
+ * slot).  A match that overshoots the window moves the next window to its end.  u16 table, zero-initialised.
  */
-int orc_lz4_compress_block_tile(const uint8_t* src, int n, uint8_t* dst, int cap, int W, int hash_log) {
-  if (n > 65536 || W > 32 || hash_log > 16) return 0;
+int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap, int hash_log) {
+  enum { W = 32 };
+  if (n > 65536 || hash_log > 16 || hash_log < 4) return 0;
   uint16_t* table = (uint16_t*)calloc((size_t)1 << hash_log, sizeof(uint16_t));
   int op = 0, anchor = 0, pos = 0;
   if (n >= LZ4_MFLIMIT + 1) {
     const int mflimit = n - LZ4_MFLIMIT;
     const int matchlimit = n - LZ4_LASTLITERALS;
     while (pos <= mflimit) {
-      int first = -1, cand_first = 0;
-      uint32_t hs[32];
-      for (int l = 0; l < W; l++) {
-        int p = pos + l;
-        hs[l] = 0xffffffffu;
+      uint32_t hs[W];
+      int cand[W], ok[W];
+      for (int r = 0; r < W; r++) {
+        int p = pos + r;
+        hs[r] = 0xffffffffu;
+        ok[r] = 0;
         if (p > mflimit) continue;
         uint32_t v = rd32(src + p);
         uint32_t h = lz4_hash(v, hash_log);
-        hs[l] = h;
-        int cand = table[h];
-        if (first < 0 && cand < p && rd32(src + cand) == v) {
-          first = l;
-          cand_first = cand;
+        hs[r] = h;
+        int c = table[h];
+        if (p > 0 && rd32(src + p - 1) == v) { /* run of one byte value: offset-1 candidate, like a sequential table */
+          ok[r] = 1;
+          cand[r] = p - 1;
+        } else if (c < p && rd32(src + c) == v) {
+          ok[r] = 1;
+          cand[r] = c;
         }
       }
-      int next;
-      if (first >= 0) {
-        int m = pos + first, c = cand_first, mlen = LZ4_MINMATCH;
+      int s = 0;
+      while (s < W) {
+        int r = s;
+        while (r < W && !ok[r]) r++;
+        if (r >= W) break;
+        int m = pos + r, c = cand[r], mlen = LZ4_MINMATCH;
         while (m + mlen < matchlimit && src[m + mlen] == src[c + mlen]) mlen++;
         op = lz4_emit_seq(src, anchor, m - anchor, m - c, mlen, dst, op, cap);
         if (op < 0) {
           free(table);
           return 0;
         }
-        next = m + mlen;
-        anchor = next;
-      } else {
-        next = pos + W;
+        anchor = m + mlen;
+        s = r + mlen;
       }
-      for (int l = 0; l < W; l++) {
-        int p = pos + l;
-        if (hs[l] != 0xffffffffu && p < next) table[hs[l]] = (uint16_t)p;
-      }
-      pos = next;
+      for (int r = 0; r < W; r++)
+        if (hs[r] != 0xffffffffu) table[hs[r]] = (uint16_t)(pos + r);
+      pos += s > W ? s : W;
     }
   }
   op = lz4_emit_seq(src, anchor, n - anchor, 0, 0, dst, op, cap);
@@ -374,7 +380,7 @@ static int64_t lz4block_compress_impl(const uint8_t* src, uint64_t n, uint32_t b
     if (ext)
       clen = ext((const char*)(src + off), (char*)tmp, (int)o, tcap);
     else if (compressor == 1)
-      clen = (o <= 65536) ? orc_lz4_compress_block_tile(src + off, (int)o, tmp, (int)o - 1, 16, 12) : 0;
+      clen = (o <= 65536) ? orc_lz4_compress_block_win(src + off, (int)o, tmp, (int)o - 1, 12) : 0;
     else
       clen = orc_lz4_compress_block(src + off, (int)o, tmp, tcap);
     int method = LZ4B_LZ4;

@@ -46,8 +46,8 @@ def lib():
         L.orc_xxh32.argtypes = [u8p, C.c_size_t, C.c_uint32]
         L.orc_lz4_compress_block.restype = C.c_int
         L.orc_lz4_compress_block.argtypes = [u8p, C.c_int, u8p, C.c_int]
-        L.orc_lz4_compress_block_tile.restype = C.c_int
-        L.orc_lz4_compress_block_tile.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+        L.orc_lz4_compress_block_win.restype = C.c_int
+        L.orc_lz4_compress_block_win.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int]
         L.orc_lz4_decompress_block.restype = C.c_int
         L.orc_lz4_decompress_block.argtypes = [u8p, C.c_int, u8p, C.c_int]
         L.orc_lz4block_bound.restype = C.c_uint64
@@ -128,12 +128,12 @@ def xxh32(b, seed=0x9747B28C):
 
 
 # ---- raw LZ4 block ----
-def lz4_compress_block(b, tile=None, hash_log=12, cap=None):
+def lz4_compress_block(b, win=False, hash_log=12, cap=None):
     a = _u8(b)
     cap = cap if cap is not None else a.size + a.size // 255 + 32
     out = np.empty(max(cap, 1), dtype=np.uint8)
-    if tile:
-        n = lib().orc_lz4_compress_block_tile(_p(a), a.size, out.ctypes.data, cap, tile, hash_log)
+    if win:
+        n = lib().orc_lz4_compress_block_win(_p(a), a.size, out.ctypes.data, cap, hash_log)
     else:
         n = lib().orc_lz4_compress_block(_p(a), a.size, out.ctypes.data, cap)
     return out[:n].tobytes() if n > 0 else None

@@ -515,7 +515,6 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0)
     return fail(B2S_E_CUDA, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-  g_lz4_tile = env_int("B2S_LZ4_TILE", g_lz4_tile);
   g_lz4_hlog = env_int("B2S_LZ4_HLOG", g_lz4_hlog);
   g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
   Context* C = new Context();

@@ -40,7 +40,7 @@ void launch_xxh32_verify(const BlockDesc* d_desc, uint32_t n_blocks, const uint8
                          uint32_t mask, int32_t* d_status, cudaStream_t st, uint64_t* launches);
 
 // ---------------- lz4.cu (K3/K4 + LZ4Block framing) ----------------
-extern int g_lz4_tile, g_lz4_hlog, g_lz4d_tile;
+extern int g_lz4_hlog, g_lz4d_tile;
 // compress every codec block into scratch (stride block_size); csize[b] = payload bytes (bit 31 = stored RAW);
 // sizes[b] = 21 + payload (input of the packing scan)
 void launch_lz4_compress(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,

@@ -8,13 +8,11 @@
 //   "LZ4Block" | token = method(0x10 RAW, 0x20 LZ4) | level | compressedLen LE32 | originalLen LE32 | XXH32&0x0FFFFFFF LE32
 // then the payload; a stream ends with a header whose three ints are zero.
 //
-// Parallelism: every codec block (<= 64 KiB here) is independent.  A *tile* of TILE lanes (8/16/32) owns one block.
-//  compress : the tile scans TILE consecutive positions per step (hash -> shared-memory u16 table -> verify 4 bytes),
-//             the lowest matching lane wins (ballot/ffs), the tile extends the match TILE bytes per ballot, emits
-//             the sequence cooperatively, then inserts the window's positions.  Deterministic; the CPU model
-//             orc_lz4_compress_block_tile() in oracle/ produces identical bytes.
-//  decompress: token chain is serial; the tile parses uniformly and copies literals / (overlapping) matches
-//             TILE bytes per step.
+// Parallelism: every codec block (<= 64 KiB here) is independent.
+//  compress : one warp per block, window-batched greedy parse (see K3 below).  Deterministic; the CPU model
+//             orc_lz4_compress_block_win() in oracle/ produces identical bytes.
+//  decompress: a tile of TILE lanes (4/8/16/32) per block; the token chain is serial, the tile parses uniformly and
+//             copies literals / (overlapping) matches TILE bytes per step.
 // This is latency/issue-bound byte-stream work (no tensor cores, HBM far from saturated by one block per tile), so
 // the levers are blocks in flight per SM (small per-tile state: 4-8 KiB hash table, no staged copy of the block)
 // and instructions per sequence.
@@ -36,39 +34,63 @@ __device__ __forceinline__ uint32_t find_stream32(const uint32_t* __restrict__ b
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K3: compress
+// K3: compress — one warp per codec block, "window-batched greedy" (specification: orc_lz4_compress_block_win)
+//
+//   per window of 32 positions:
+//     1. every lane hashes its 4 bytes, reads the candidate from the shared-memory table (state before the window;
+//        byte runs use an explicit offset-1 candidate), verifies 4 bytes and measures the match locally up to
+//        8 bytes                                                                          (all lanes in parallel)
+//     2. the warp walks the window greedily with uniform bit operations on the ballot mask: lowest matching
+//        position >= cursor, its length by shuffle (cooperative extension only when the local 8 bytes were all
+//        equal) — about a dozen instructions per selected sequence
+//     3. literal counts, encoded sizes and output offsets of all selected sequences by one warp suffix-sum
+//     4. each selected lane emits its own sequence (token, <= 16 literals, offset, <= 2 length bytes); rare longer
+//        literal runs / lengths go through a cooperative slow path
+//     5. all 32 positions are inserted; a slot hit twice is settled by a read-back so the highest position wins
+//   Measured motivation (profiles/): terasort-shaped data has ~4400 sequences per 32 KiB block (7.5 B each), so the
+//   per-sequence instruction count is what bounds this kernel, not HBM.
 // ------------------------------------------------------------------------------------------------------------
-template <int TILE>
-__device__ __forceinline__ void tile_store_len_ext(uint8_t* o, int nb, int r, int lane) {
-  // nb bytes: 255 ... 255, r - 255*(nb-1)
-  for (int j = lane; j < nb; j += TILE) o[j] = (j == nb - 1) ? (uint8_t)(r - 255 * (nb - 1)) : (uint8_t)255;
+__device__ __forceinline__ void warp_store_len_ext(uint8_t* o, int nb, int r, int lane) {
+  for (int j = lane; j < nb; j += 32) o[j] = (j == nb - 1) ? (uint8_t)(r - 255 * (nb - 1)) : (uint8_t)255;
 }
-
-template <int TILE>
-__device__ __forceinline__ void tile_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int n,
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int n,
                                                 int lane) {
   if (n >= 96) {
-    group_copy<TILE>(dst, src, (uint32_t)n, lane);
+    group_copy<32>(dst, src, (uint32_t)n, lane);
   } else {
-    for (int j = lane; j < n; j += TILE) dst[j] = __ldg(src + j);
+    for (int j = lane; j < n; j += 32) dst[j] = __ldg(src + j);
   }
 }
-
-template <int TILE, int HLOG>
-__global__ void __launch_bounds__(kLz4Threads) lz4_compress_kernel(
+// cooperative emit of one sequence (mlen == 0: final literal run without a match part)
+__device__ __forceinline__ void warp_emit_seq(uint8_t* __restrict__ o, const uint8_t* __restrict__ lit_src, int lit,
+                                              int off, int mlen, int lane) {
+  const int ml = mlen - kMinMatch;
+  const int nbL = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+  if (lane == 0) o[0] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mlen ? (ml < 15 ? ml : 15) : 0));
+  if (nbL) warp_store_len_ext(o + 1, nbL, lit - 15, lane);
+  warp_copy_bytes(o + 1 + nbL, lit_src, lit, lane);
+  if (mlen) {
+    uint8_t* q = o + 1 + nbL + lit;
+    if (lane == 0) q[0] = (uint8_t)off;
+    if (lane == 1) q[1] = (uint8_t)(off >> 8);
+    if (ml >= 15) warp_store_len_ext(q + 2, (ml - 15) / 255 + 1, ml - 15, lane);
+  }
+}
+template <int HLOG>
+__global__ void __launch_bounds__(kLz4Threads, (HLOG >= 13 ? 3 : HLOG == 12 ? 6 : 8)) lz4_compress_kernel(
     const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
     const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
     uint8_t* __restrict__ scratch, uint32_t* __restrict__ csize, uint64_t* __restrict__ sizes,
     unsigned int* __restrict__ work_counter) {
   extern __shared__ __align__(16) uint16_t smem_tables[];
-  const int lane = threadIdx.x % TILE;
-  const int tile_in_cta = threadIdx.x / TILE;
-  uint16_t* table = smem_tables + (size_t)tile_in_cta * (1 << HLOG);
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  uint16_t* table = smem_tables + (size_t)(threadIdx.x >> 5) * (1 << HLOG);
 
   for (;;) {
     uint32_t b = 0;
     if (lane == 0) b = atomicAdd(work_counter, 1u);
-    b = tile_shfl<TILE>(b, 0);
+    b = __shfl_sync(FULL, b, 0);
     if (b >= n_blocks) break;
 
     const uint32_t si = find_stream32(blk_base, n_streams, b);
@@ -79,12 +101,11 @@ __global__ void __launch_bounds__(kLz4Threads) lz4_compress_kernel(
     uint8_t* __restrict__ out = scratch + (uint64_t)b * block_size;
     const int cap = n - 1;  // LZ4BlockOutputStream stores RAW when compressedLength >= originalLength
 
-    // zero the table (16 bytes per lane per step)
     {
       uint4* t4 = reinterpret_cast<uint4*>(table);
-      for (int j = lane; j < (1 << HLOG) / 8; j += TILE) t4[j] = make_uint4(0, 0, 0, 0);
+      for (int j = lane; j < (1 << HLOG) / 8; j += 32) t4[j] = make_uint4(0, 0, 0, 0);
     }
-    tile_sync<TILE>();
+    __syncwarp();
 
     int op = 0, anchor = 0, pos = 0;
     bool fail = false;
@@ -92,85 +113,166 @@ __global__ void __launch_bounds__(kLz4Threads) lz4_compress_kernel(
       const int mflimit = n - kMFLimit;
       const int matchlimit = n - kLastLiterals;
       while (pos <= mflimit) {
-        const int p = pos + lane;
+        // ---- 1. lookup + local match length (<= 8) for all 32 positions.  Lane l owns window position r = 31 - l:
+        //         the hardware resolves same-address shared stores in favour of the lowest lane, so with this
+        //         mapping a contested hash slot receives the highest position on the first store (step 4).
+        const int r_me = 31 - lane;
+        const int p = pos + r_me;
         const bool valid = p <= mflimit;
-        const uint32_t v = valid ? ld32u_ro(s + p) : 0u;
-        const uint32_t h = (v * 2654435761u) >> (32 - HLOG);
-        const int cand = table[h];
-        const bool ok = valid && cand < p && ld32u_ro(s + cand) == v;
-        const unsigned bal = tile_ballot<TILE>(ok);
-        int next;
-        if (bal) {
-          const int first = __ffs(bal) - 1;
-          const int m = pos + first;
-          const int c = tile_shfl<TILE>(cand, first);
-          // forward extension, TILE bytes per ballot
-          int mlen;
-          {
-            const int maxl = matchlimit - m;
-            int k = kMinMatch + lane;
-            for (;;) {
-              const bool ne = (k >= maxl) || (__ldg(s + m + k) != __ldg(s + c + k));
-              const unsigned nb = tile_ballot<TILE>(ne);
-              if (nb) {
-                mlen = k - lane + __ffs(nb) - 1;
-                break;
-              }
-              k += TILE;
+        uint32_t v = 0, v2 = 0, h = 0;
+        int cand = 0, ml = 0;
+        bool ok = false;
+        if (valid) {
+          const uintptr_t a = reinterpret_cast<uintptr_t>(s + p);
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+          const unsigned sh = (a & 3u) * 8u;
+          const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = sh ? __ldg(w + 2) : 0u;
+          v = __funnelshift_r(w0, w1, sh);
+          v2 = __funnelshift_r(w1, w2, sh);
+          h = (v * 2654435761u) >> (32 - HLOG);
+          cand = table[h];
+          const uint32_t prev = p > 0 ? (uint32_t)__ldg(s + p - 1) : (~v & 0xffu);
+          uint32_t x = 1;
+          if (v == prev * 0x01010101u) {  // byte run: offset-1 candidate (what a sequential hash table would hold)
+            ok = true;
+            cand = p - 1;
+            x = __funnelshift_r(v, v2, 24) ^ v2;  // bytes p+3..p+6 against p+4..p+7
+          } else if (cand < p) {
+            const uintptr_t ca = reinterpret_cast<uintptr_t>(s + cand);
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(ca & ~uintptr_t(3));
+            const unsigned csh = (ca & 3u) * 8u;
+            const uint32_t c0 = __ldg(cw), c1 = __ldg(cw + 1);
+            if (__funnelshift_r(c0, c1, csh) == v) {
+              ok = true;
+              const uint32_t c2 = csh ? __ldg(cw + 2) : 0u;
+              x = __funnelshift_r(c1, c2, csh) ^ v2;
             }
           }
-          // emit: token | litlen ext | literals | offset | matchlen ext
-          const int lit = m - anchor;
-          const int ml = mlen - kMinMatch;
-          const int nbL = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
-          const int nbM = ml >= 15 ? (ml - 15) / 255 + 1 : 0;
-          const int need = 1 + nbL + lit + 2 + nbM;
-          if (op + need > cap) {
-            fail = true;
-            break;
+          if (ok) {
+            ml = x ? 4 + ((__ffs(x) - 1) >> 3) : 8;
+            const int lim = matchlimit - p;
+            if (ml > lim) ml = lim;
           }
-          uint8_t* o = out + op;
-          if (lane == 0) o[0] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (ml < 15 ? ml : 15));
-          if (nbL) tile_store_len_ext<TILE>(o + 1, nbL, lit - 15, lane);
-          tile_copy_bytes<TILE>(o + 1 + nbL, s + anchor, lit, lane);
-          uint8_t* q = o + 1 + nbL + lit;
-          const int off = m - c;
-          if (lane == 0) q[0] = (uint8_t)off;
-          if (lane == 1 % TILE) q[1] = (uint8_t)(off >> 8);
-          if (nbM) tile_store_len_ext<TILE>(q + 2, nbM, ml - 15, lane);
-          op += need;
-          next = m + mlen;
-          anchor = next;
-        } else {
-          next = pos + TILE;
         }
-        tile_sync<TILE>();  // all lanes have read the table for this window
-        // insert the window's positions that precede the next scan position.  Two lanes may hash to one slot and the
-        // hardware's same-address store winner is unspecified, so losers with a *later* position re-store until the
-        // slot holds the highest position (= what a sequential scan would leave).  Usually one read-back, no retry.
-        const bool ins = valid && p < next;
-        if (ins) table[h] = (uint16_t)p;
-        tile_sync<TILE>();
+        const unsigned posmask = __brev(__ballot_sync(FULL, ok));  // bit r <-> window position r
+
+        // ---- 2. greedy walk over the window: uniform bit operations, ~a dozen instructions per selected sequence
+        int cur = 0;          // window-relative parse cursor
+        unsigned selmask = 0; // positions whose match the parse takes
         for (;;) {
-          const bool lost = ins && table[h] < (uint16_t)p;
-          if (!tile_ballot<TILE>(lost)) break;
-          if (lost) table[h] = (uint16_t)p;
-          tile_sync<TILE>();
+          const unsigned t = posmask & (FULL << cur);
+          if (!t) break;
+          const int r = __ffs(t) - 1;
+          int mlr = __shfl_sync(FULL, ml, 31 - r);
+          if (mlr == 8) {  // local 8 bytes all equal: extend cooperatively, 32 bytes per ballot
+            const int m = pos + r;
+            const int maxl = matchlimit - m;
+            if (maxl > 8) {
+              const int c = __shfl_sync(FULL, cand, 31 - r);
+              int k = 8 + lane;
+              for (;;) {
+                const bool ne = (k >= maxl) || (__ldg(s + m + k) != __ldg(s + c + k));
+                const unsigned nb = __ballot_sync(FULL, ne);
+                if (nb) {
+                  mlr = k - lane + __ffs(nb) - 1;
+                  break;
+                }
+                k += 32;
+              }
+              if (r == r_me) ml = mlr;
+            }
+          }
+          selmask |= 1u << r;
+          cur = r + mlr;
+          if (cur >= 32) break;
         }
-        pos = next;
+
+        // ---- 3. sizes and output offsets for all selected sequences at once (suffix sum over lanes = prefix over positions)
+        const bool sel = (selmask >> r_me) & 1u;
+        const unsigned below = selmask & ((1u << r_me) - 1u);  // selected positions before mine
+        const int rp = 31 - __clz(below);                      // -1 when none
+        const int ml_prev = __shfl_sync(FULL, ml, below ? 31 - rp : lane);
+        const int lit = p - (below ? pos + rp + ml_prev : anchor);
+        const int mlc = ml - kMinMatch;
+        int sz = 0;
+        if (sel) {
+          sz = 3 + lit;
+          if (lit >= 15) sz += (lit - 15) / 255 + 1;
+          if (mlc >= 15) sz += (mlc - 15) / 255 + 1;
+        }
+        int suf = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_down_sync(FULL, suf, d);
+          if (lane + d < 32) suf += t;
+        }
+        const int total = __shfl_sync(FULL, suf, 0);
+        if (op + total > cap) {
+          fail = true;
+          break;
+        }
+        const int my_op = op + suf - sz;  // sequences at earlier positions (higher lanes) come first
+
+        // ---- 4. emit: every selected lane writes its own sequence; only very long literal runs / lengths go cooperative
+        bool slow = false;
+        if (sel) {
+          if (lit <= 16 && mlc < 15 + 510) {
+            uint8_t* q = out + my_op;
+            *q++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mlc < 15 ? mlc : 15));
+            if (lit >= 15) *q++ = (uint8_t)(lit - 15);
+            const uint8_t* ls = s + p - lit;
+            for (int j = 0; j < lit; j++) q[j] = __ldg(ls + j);
+            q += lit;
+            const int off = p - cand;
+            q[0] = (uint8_t)off;
+            q[1] = (uint8_t)(off >> 8);
+            if (mlc >= 15) {
+              int rem = mlc - 15;
+              q += 2;
+              if (rem >= 255) {
+                *q++ = 255;
+                rem -= 255;
+              }
+              *q = (uint8_t)rem;
+            }
+          } else {
+            slow = true;
+          }
+        }
+        unsigned slowmask = __ballot_sync(FULL, slow);
+        while (slowmask) {
+          const int l = __ffs(slowmask) - 1;
+          slowmask &= slowmask - 1;
+          const int lit_r = __shfl_sync(FULL, lit, l);
+          const int ml_r = __shfl_sync(FULL, ml, l);
+          const int op_r = __shfl_sync(FULL, my_op, l);
+          const int cand_r = __shfl_sync(FULL, cand, l);
+          const int m = pos + 31 - l;
+          warp_emit_seq(out + op_r, s + m - lit_r, lit_r, m - cand_r, ml_r, lane);
+        }
+        op += total;
+        if (selmask) anchor = pos + cur;
+
+        // ---- 5. insert the window; a read-back settles slots hit twice so that the highest position wins
+        __syncwarp();
+        if (valid) table[h] = (uint16_t)p;
+        __syncwarp();
+        for (;;) {
+          const bool lost = valid && table[h] < (uint16_t)p;
+          if (!__ballot_sync(FULL, lost)) break;
+          if (lost) table[h] = (uint16_t)p;
+          __syncwarp();
+        }
+        pos += cur > 32 ? cur : 32;
       }
     }
     if (!fail) {
       const int lit = n - anchor;
-      const int nbL = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
-      const int need = 1 + nbL + lit;
+      const int need = 1 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);
       if (op + need > cap) {
         fail = true;
       } else {
-        uint8_t* o = out + op;
-        if (lane == 0) o[0] = (uint8_t)((lit < 15 ? lit : 15) << 4);
-        if (nbL) tile_store_len_ext<TILE>(o + 1, nbL, lit - 15, lane);
-        tile_copy_bytes<TILE>(o + 1 + nbL, s + anchor, lit, lane);
+        warp_emit_seq(out + op, s + anchor, lit, 0, 0, lane);
         op += need;
       }
     }
@@ -178,36 +280,35 @@ __global__ void __launch_bounds__(kLz4Threads) lz4_compress_kernel(
       csize[b] = fail ? ((uint32_t)n | 0x80000000u) : (uint32_t)op;
       sizes[b] = 21u + (uint64_t)(fail ? n : op);
     }
-    tile_sync<TILE>();
+    __syncwarp();
   }
 }
 
-template <int TILE, int HLOG>
+template <int HLOG>
 static void launch_lz4_compress_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                                   const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks,
                                   uint32_t block_size, uint8_t* d_scratch, uint32_t* d_csize, uint64_t* d_sizes,
                                   unsigned int* d_counter, cudaStream_t st) {
-  constexpr int kTiles = kLz4Threads / TILE;
-  const size_t smem = (size_t)kTiles * (2u << HLOG);
+  constexpr int kWarps = kLz4Threads / 32;
+  const size_t smem = (size_t)kWarps * (2u << HLOG);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(lz4_compress_kernel<TILE, HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(lz4_compress_kernel<HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_compress_kernel<TILE, HLOG>, kLz4Threads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_compress_kernel<HLOG>, kLz4Threads, smem);
   if (per_sm < 1) per_sm = 1;
-  uint64_t want = ((uint64_t)n_blocks + kTiles - 1) / kTiles;
+  uint64_t want = ((uint64_t)n_blocks + kWarps - 1) / kWarps;
   uint64_t grid = (uint64_t)kSMs * per_sm;
   if (grid > want) grid = want;
-  lz4_compress_kernel<TILE, HLOG><<<(unsigned)grid, kLz4Threads, smem, st>>>(
-      src_base, d_src_off, d_src_len, d_blk_base, n_streams, n_blocks, block_size, d_scratch, d_csize, d_sizes,
-      d_counter);
+  lz4_compress_kernel<HLOG><<<(unsigned)grid, kLz4Threads, smem, st>>>(src_base, d_src_off, d_src_len, d_blk_base,
+                                                                      n_streams, n_blocks, block_size, d_scratch,
+                                                                      d_csize, d_sizes, d_counter);
 }
 
-int g_lz4_tile = 16;   // tuning knobs (api.cu reads B2S_LZ4_TILE / B2S_LZ4_HLOG / B2S_LZ4D_TILE once at init)
-int g_lz4_hlog = 12;
-int g_lz4d_tile = 16;
+int g_lz4_hlog = 12;   // tuning knobs (api.cu reads B2S_LZ4_HLOG / B2S_LZ4D_TILE once at init); 12 is the specified default
+int g_lz4d_tile = 8;
 
 void launch_lz4_compress(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                          const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
@@ -215,20 +316,14 @@ void launch_lz4_compress(const uint8_t* src_base, const uint64_t* d_src_off, con
                          cudaStream_t st, uint64_t* launches) {
   if (!n_blocks) return;
   cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), st);
-#define B2S_LZ4C(T, H)                                                                                              \
-  launch_lz4_compress_t<T, H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, n_blocks, block_size, d_scratch, \
-                              d_csize, d_sizes, d_counter, st)
-  const int key = g_lz4_tile * 100 + g_lz4_hlog;
-  switch (key) {
-    case 811: B2S_LZ4C(8, 11); break;
-    case 812: B2S_LZ4C(8, 12); break;
-    case 1611: B2S_LZ4C(16, 11); break;
-    case 1613: B2S_LZ4C(16, 13); break;
-    case 3211: B2S_LZ4C(32, 11); break;
-    case 3212: B2S_LZ4C(32, 12); break;
-    case 3213: B2S_LZ4C(32, 13); break;
-    case 1612:
-    default: B2S_LZ4C(16, 12); break;
+#define B2S_LZ4C(H)                                                                                                  \
+  launch_lz4_compress_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, n_blocks, block_size, d_scratch,  \
+                           d_csize, d_sizes, d_counter, st)
+  switch (g_lz4_hlog) {
+    case 10: B2S_LZ4C(10); break;
+    case 11: B2S_LZ4C(11); break;
+    case 13: B2S_LZ4C(13); break;
+    default: B2S_LZ4C(12); break;
   }
 #undef B2S_LZ4C
   *launches += 1;
@@ -442,6 +537,13 @@ void launch_lz4block_fill(const uint8_t* src_base, const uint64_t* d_src_off, co
 
 // ------------------------------------------------------------------------------------------------------------
 // K4: decompress (LZ4_decompress_fast semantics: driven by originalLen, must consume exactly compressedLen)
+//
+// A warp carries 32/TILE independent blocks ("tiles" of TILE lanes) through ONE warp-uniform instruction stream:
+// every iteration decodes one sequence per tile (token, literal run, offset, match), with the copy loops bounded by
+// the warp-wide maximum (REDUX.MAX) and predicated per tile.  All synchronisation is full-mask __syncwarp().
+// (Per-tile control flow with partial-mask sync looked natural but ptxas guards every non-uniform-mask
+// __syncwarp/__ballot with MATCH.ANY — measured at ~1 per 50 cycles per SM on B200, profiles/ — so it is avoided.)
+// Sequences in shuffle data are short (terasort: 0.8 literal + 6.7 match bytes), hence small tiles.
 // ------------------------------------------------------------------------------------------------------------
 template <int TILE>
 __global__ void __launch_bounds__(kLz4Threads) lz4_decompress_kernel(const BlockDesc* __restrict__ desc,
@@ -450,79 +552,125 @@ __global__ void __launch_bounds__(kLz4Threads) lz4_decompress_kernel(const Block
                                                                      uint8_t* __restrict__ dst_base,
                                                                      int32_t* __restrict__ status,
                                                                      unsigned int* __restrict__ work_counter) {
-  const int lane = threadIdx.x % TILE;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int tl = threadIdx.x % TILE;  // lane within the tile
+  bool active = false, exhausted = false;
+  const uint8_t* __restrict__ in = nullptr;
+  uint8_t* out = nullptr;
+  int ip = 0, op = 0, clen = 0, olen = 0;
+  uint32_t stream = 0;
+
   for (;;) {
-    uint32_t b = 0;
-    if (lane == 0) b = atomicAdd(work_counter, 1u);
-    b = tile_shfl<TILE>(b, 0);
-    if (b >= n_blocks) break;
-    const BlockDesc d = desc[b];
-    const int olen = (int)d.olen, clen = (int)d.clen;
-    if (olen == 0) continue;
-    const uint8_t* __restrict__ in = src_base + d.src;
-    uint8_t* out = dst_base + d.dst;
-    if (d.stream & 0x80000000u) {  // stored RAW
-      group_copy<TILE>(out, in, (uint32_t)olen, lane);
-      continue;
-    }
-    int ip = 0, op = 0;
-    bool err = false;
-    for (;;) {
-      if (ip >= clen) { err = true; break; }
-      const int token = __ldg(in + ip++);
-      int ll = token >> 4;
-      if (ll == 15) {
-        int bb;
-        do {
-          if (ip >= clen) { err = true; break; }
-          bb = __ldg(in + ip++);
-          ll += bb;
-        } while (bb == 255);
-        if (err) break;
-      }
-      if (ll > olen - op || ll > clen - ip) { err = true; break; }
-      if (ll >= 96) {
-        group_copy<TILE>(out + op, in + ip, (uint32_t)ll, lane);
+    // ---- refill tiles that have no block (rare: once per codec block)
+    if (!active && !exhausted) {
+      uint32_t b = 0;
+      if (tl == 0) b = atomicAdd(work_counter, 1u);
+      b = __shfl_sync(tile_mask<TILE>(), b, 0, TILE);
+      if (b >= n_blocks) {
+        exhausted = true;
       } else {
-        for (int j = lane; j < ll; j += TILE) out[op + j] = __ldg(in + ip + j);
-      }
-      op += ll;
-      ip += ll;
-      if (olen - op < kMFLimit) {
-        if (op != olen) err = true;  // last match must start >= 12 bytes before the end of the block
-        break;
-      }
-      if (ip + 2 > clen) { err = true; break; }
-      const int off = __ldg(in + ip) | (__ldg(in + ip + 1) << 8);
-      ip += 2;
-      int ml = token & 15;
-      if (ml == 15) {
-        int bb;
-        do {
-          if (ip >= clen) { err = true; break; }
-          bb = __ldg(in + ip++);
-          ml += bb;
-        } while (bb == 255);
-        if (err) break;
-      }
-      ml += kMinMatch;
-      if (ml > olen - op || off == 0 || off > op) { err = true; break; }
-      tile_sync<TILE>();  // literals of this sequence visible to the whole tile
-      {
-        const uint8_t* msrc = out + op - off;
-        if (off >= ml) {
-          for (int j = lane; j < ml; j += TILE) out[op + j] = msrc[j];
-        } else {
-          // overlapping match: every byte comes from the already complete window [op-off, op)
-          for (int j = lane; j < ml; j += TILE) out[op + j] = msrc[j % off];
+        const BlockDesc d = desc[b];
+        if (d.olen != 0) {
+          in = src_base + d.src;
+          out = dst_base + d.dst;
+          if (d.stream & 0x80000000u) {  // stored RAW
+            group_copy<TILE>(out, in, d.olen, tl);
+          } else {
+            active = true;
+            ip = op = 0;
+            clen = (int)d.clen;
+            olen = (int)d.olen;
+            stream = d.stream;
+          }
         }
       }
-      op += ml;
-      tile_sync<TILE>();
-      if (olen - op < kLastLiterals) { err = true; break; }
     }
-    if (err || ip != clen) {
-      if (lane == 0) set_status(status, d.stream & 0x7fffffffu, B2S_E_CORRUPT);
+    if (__all_sync(FULL, exhausted && !active)) break;
+
+    // ---- one sequence per active tile, warp-uniform control flow
+    bool err = false;
+    int token = 0, ll = 0;
+    if (active) {
+      if (ip >= clen) err = true;
+      else {
+        token = __ldg(in + ip++);
+        ll = token >> 4;
+      }
+    }
+    bool more = active && !err && ll == 15;
+    while (__any_sync(FULL, more)) {
+      if (more) {
+        if (ip >= clen) {
+          err = true;
+          more = false;
+        } else {
+          const int bb = __ldg(in + ip++);
+          ll += bb;
+          more = (bb == 255);
+        }
+      }
+    }
+    if (active && !err && (ll > olen - op || ll > clen - ip)) err = true;
+    {
+      const int cl = (active && !err) ? ll : 0;
+      const int maxl = __reduce_max_sync(FULL, cl);
+      for (int j = tl; j < maxl; j += TILE)
+        if (j < cl) out[op + j] = __ldg(in + ip + j);
+    }
+    if (active && !err) {
+      op += ll;
+      ip += ll;
+    }
+    const bool last = active && !err && (olen - op < kMFLimit);  // last match must start >= 12 bytes before the end
+    if (last && (op != olen || ip != clen)) err = true;
+    const bool cont = active && !err && !last;
+    int off = 0, ml = 0;
+    if (cont) {
+      if (ip + 2 > clen) err = true;
+      else {
+        off = __ldg(in + ip) | (__ldg(in + ip + 1) << 8);
+        ip += 2;
+        ml = token & 15;
+      }
+    }
+    more = cont && !err && ml == 15;
+    while (__any_sync(FULL, more)) {
+      if (more) {
+        if (ip >= clen) {
+          err = true;
+          more = false;
+        } else {
+          const int bb = __ldg(in + ip++);
+          ml += bb;
+          more = (bb == 255);
+        }
+      }
+    }
+    if (cont && !err) {
+      ml += kMinMatch;
+      if (ml > olen - op || off == 0 || off > op) err = true;
+    }
+    __syncwarp();  // literals of this sequence are visible to the whole warp
+    {
+      const int cm = (cont && !err) ? ml : 0;
+      const int maxm = __reduce_max_sync(FULL, cm);
+      const uint8_t* msrc = out + op - off;
+      for (int j = tl; j < maxm; j += TILE) {
+        if (j < cm) {
+          // overlapping match (off < ml): every byte comes from the already complete window [op-off, op)
+          const int k = (j >= off) ? (int)((unsigned)j % (unsigned)off) : j;
+          out[op + j] = msrc[k];
+        }
+      }
+    }
+    if (cont && !err) {
+      op += ml;
+      if (olen - op < kLastLiterals) err = true;  // the last 5 bytes of a block are literals
+    }
+    __syncwarp();
+    if (active && (err || last)) {
+      if (err && tl == 0) set_status(status, stream & 0x7fffffffu, B2S_E_CORRUPT);
+      active = false;
     }
   }
 }
@@ -546,9 +694,10 @@ void launch_lz4_decompress(const BlockDesc* d_desc, uint32_t n_blocks, const uin
   if (!n_blocks) return;
   cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), st);
   switch (g_lz4d_tile) {
-    case 8: launch_lz4_decompress_t<8>(d_desc, n_blocks, src_base, dst_base, d_status, d_counter, st); break;
+    case 4: launch_lz4_decompress_t<4>(d_desc, n_blocks, src_base, dst_base, d_status, d_counter, st); break;
+    case 16: launch_lz4_decompress_t<16>(d_desc, n_blocks, src_base, dst_base, d_status, d_counter, st); break;
     case 32: launch_lz4_decompress_t<32>(d_desc, n_blocks, src_base, dst_base, d_status, d_counter, st); break;
-    default: launch_lz4_decompress_t<16>(d_desc, n_blocks, src_base, dst_base, d_status, d_counter, st); break;
+    default: launch_lz4_decompress_t<8>(d_desc, n_blocks, src_base, dst_base, d_status, d_counter, st); break;
   }
   *launches += 1;
 }
