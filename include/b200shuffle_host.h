@@ -1,0 +1,86 @@
+/*
+ * b200shuffle_host.h — C entry points of libb200shuffle_host.so: the HOST-SIDE MIRROR of the reference's plugin
+ * surface for the codec path, written in C++ because the reference is compiled (Scala/JVM) code and no JVM exists
+ * in this image.  It sits *above* the C ABI of include/b200shuffle.h exactly where the Scala classes sit above the
+ * JNI shim, keeps their names, argument meaning, on-disk layout and error behaviour, and exists so
+ * that parity tests can read like the reference's own tests (src/test/scala/org/apache/spark/shuffle/S3ShuffleManagerTest.scala).
+ *
+ * Mirrored classes (C++ in spark-s3-shuffle_b200/host/, namespace b2s::host):
+ *   S3ShuffleDispatcher        helper/S3ShuffleDispatcher.scala:39-70 (config), :120-144 (paths), :190-237 (open/create)
+ *   S3ShuffleHelper            helper/S3ShuffleHelper.scala:44-59 (.index/.checksum), :67-92 (cached readers), :94-103 (algorithms)
+ *   S3ShuffleMapOutputWriter   shuffle/S3ShuffleMapOutputWriter.scala:67-83 (getPartitionWriter), :91-118 (commitAllPartitions),
+ *                              :168-202 (partition stream), + the GPU "compress on commit" mode of SURVEY.md §3.2 option B
+ *   S3ShuffleReader            storage/S3ShuffleReader.scala:77-110 (block list -> prefetch -> verify -> decompress),
+ *                              storage/S3ShuffleBlockIterator.scala:36-43, storage/S3ShuffleBlockStream.scala:36-40,73-92
+ * Only file:// roots are implemented (S3/Hadoop I/O is out of scope).
+ *
+ * Errors: functions return 0 or a negative B2SH_E_* code; b2sh_last_error() holds the reference's exception text
+ * (e.g. "Precondition: Expect a monotonically increasing reducePartitionId.", "Invalid checksum detected for shuffle_0_1_2").
+ */
+#ifndef B200SHUFFLE_HOST_H
+#define B200SHUFFLE_HOST_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2SH_OK 0
+#define B2SH_E_RUNTIME (-101)     /* RuntimeException (preconditions, length mismatch)                   */
+#define B2SH_E_IO (-102)          /* IOException (closed stream, "Stream is corrupted")                  */
+#define B2SH_E_SPARK (-103)       /* SparkException (invalid checksum, unexpected file length)           */
+#define B2SH_E_UNSUPPORTED (-104) /* UnsupportedOperationException (unknown checksum algorithm / codec)  */
+#define B2SH_E_CODEC (-105)       /* the C ABI below reported a call-level failure (no GPU, CUDA error)  */
+
+const char* b2sh_last_error(void);
+
+/* ---- dispatcher: conf is "key=value\n" lines using the reference's keys (spark.shuffle.s3.rootDir, .bufferSize,
+ * .folderPrefixes, .alwaysCreateIndex, .cleanup, spark.shuffle.checksum.enabled/.algorithm, spark.io.compression.codec,
+ * spark.io.compression.lz4.blockSize, spark.app.id) plus the additive spark.shuffle.s3.gpu.enabled (default true). ---- */
+typedef struct b2sh_dispatcher b2sh_dispatcher;
+int b2sh_dispatcher_create(const char* conf, b2sh_dispatcher** out);
+void b2sh_dispatcher_destroy(b2sh_dispatcher* d);
+/* kind: 0 = .data, 1 = .index, 2 = .checksum ; writes the path (helper/S3ShuffleDispatcher.scala:142-143) into buf */
+int b2sh_dispatcher_get_path(b2sh_dispatcher* d, int kind, int32_t shuffle_id, int64_t map_id, char* buf, uint32_t cap);
+int b2sh_dispatcher_remove_shuffle(b2sh_dispatcher* d, int32_t shuffle_id);
+
+/* ---- helper ---- */
+int b2sh_helper_checksum_algorithm(const char* name); /* -> B2S_CHECKSUM_* id or B2SH_E_UNSUPPORTED */
+int b2sh_helper_get_partition_lengths(b2sh_dispatcher* d, int32_t shuffle_id, int64_t map_id, int64_t* out,
+                                      uint32_t cap, uint32_t* count); /* the cumulative offsets stored in .index */
+int b2sh_helper_get_checksums(b2sh_dispatcher* d, int32_t shuffle_id, int64_t map_id, int64_t* out, uint32_t cap,
+                              uint32_t* count);
+
+/* ---- map output writer ---- */
+typedef struct b2sh_writer b2sh_writer;
+int b2sh_writer_create(b2sh_dispatcher* d, int32_t shuffle_id, int64_t map_id, int32_t num_partitions,
+                       b2sh_writer** out);
+/* getPartitionWriter(reducePartitionId).openStream().write(bytes): ids must increase monotonically */
+int b2sh_writer_open_partition(b2sh_writer* w, int32_t reduce_id);
+int b2sh_writer_write(b2sh_writer* w, const uint8_t* bytes, uint64_t n);
+int b2sh_writer_close_partition(b2sh_writer* w);
+/* commitAllPartitions: GPU mode compresses + checksums every partition in one batch, then writes .data/.index/.checksum.
+ * checksums_in is used only in pass-through mode (spark.shuffle.s3.gpu.enabled=false: bytes arrive already compressed,
+ * exactly the reference's behaviour).  partition_lengths_out receives num_partitions values (MapOutputCommitMessage). */
+int b2sh_writer_commit_all_partitions(b2sh_writer* w, const int64_t* checksums_in, int64_t* partition_lengths_out);
+int b2sh_writer_abort(b2sh_writer* w);
+void b2sh_writer_destroy(b2sh_writer* w);
+
+/* ---- reader: blocks [start_partition, end_partition) of the given maps ---- */
+typedef struct b2sh_reader b2sh_reader;
+int b2sh_reader_create(b2sh_dispatcher* d, int32_t shuffle_id, const int64_t* map_ids, uint32_t n_maps,
+                       int32_t start_partition, int32_t end_partition, int do_batch_fetch, b2sh_reader** out);
+/* read(): resolves block ranges from .index, drops empty blocks, fetches the remaining ones, verifies every
+ * partition slice against .checksum and decompresses — all blocks of the task in one C-ABI batch.  Afterwards
+ * block k's decoded stream is at data + off[k].  A checksum mismatch returns B2SH_E_SPARK with the reference's message,
+ * a malformed stream B2SH_E_IO. */
+int b2sh_reader_read(b2sh_reader* r, uint32_t* n_blocks);
+int b2sh_reader_block(b2sh_reader* r, uint32_t k, int64_t* map_id, int32_t* start_reduce, int32_t* end_reduce,
+                      const uint8_t** data, uint64_t* len);
+uint64_t b2sh_reader_remote_bytes_read(b2sh_reader* r); /* metric parity with storage/S3ShuffleReader.scala:94-95 */
+void b2sh_reader_destroy(b2sh_reader* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

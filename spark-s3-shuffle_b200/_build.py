@@ -12,6 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200shuffle.so")
+HOST_LIB = os.path.join(HERE, "libb200shuffle_host.so")
+HOST_SRC = os.path.join(HERE, "host", "shuffle_host.cpp")
 SOURCES = ["api.cu", "scan.cu", "checksum.cu", "xxh32.cu", "lz4.cu", "gen.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -73,5 +75,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_host(force=False):
+    """libb200shuffle_host.so: the C++ host mirror of the reference's writer/reader/helper classes, linked against
+    the C ABI (g++ only; it contains no device code)."""
+    lib = build(force=force)
+    deps = [HOST_SRC, os.path.join(HERE, "..", "include", "b200shuffle_host.h"),
+            os.path.join(HERE, "..", "include", "b200shuffle.h"), lib]
+    if not force and os.path.exists(HOST_LIB) and os.path.getmtime(HOST_LIB) >= max(os.path.getmtime(d) for d in deps):
+        return HOST_LIB
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB, HOST_SRC, "-L" + HERE,
+           "-l:libb200shuffle.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host library build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

@@ -1,0 +1,628 @@
+// shuffle_host.cpp — host-side mirror (C++) of the reference's plugin classes on the codec path, above the C ABI.
+// See include/b200shuffle_host.h for the class ↔ reference file:line map.  Only file:// roots; S3 I/O is out of scope.
+#include "../../include/b200shuffle_host.h"
+
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200shuffle.h"
+
+namespace b2s {
+namespace host {
+
+// ---- exception types named after what the reference throws -----------------------------------------------
+struct RuntimeException : std::runtime_error { using std::runtime_error::runtime_error; };
+struct IOException : std::runtime_error { using std::runtime_error::runtime_error; };
+struct SparkException : std::runtime_error { using std::runtime_error::runtime_error; };
+struct UnsupportedOperationException : std::runtime_error { using std::runtime_error::runtime_error; };
+struct CodecException : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// ---- block ids (org.apache.spark.storage.BlockId names) ---------------------------------------------------
+struct BlockId {
+  enum Kind { Shuffle, ShuffleBatch, Data, Index, Checksum } kind;
+  int32_t shuffleId;
+  int64_t mapId;
+  int32_t reduceId;     // start reduce id for ShuffleBatch
+  int32_t endReduceId;  // ShuffleBatch only
+  std::string name() const {
+    std::ostringstream o;
+    o << "shuffle_" << shuffleId << "_" << mapId << "_" << reduceId;
+    switch (kind) {
+      case ShuffleBatch: o << "_" << endReduceId; break;
+      case Data: o << ".data"; break;
+      case Index: o << ".index"; break;
+      case Checksum: o << ".checksum"; break;
+      default: break;
+    }
+    return o.str();
+  }
+};
+
+// ---- pinned byte arena (what the JVM side wraps as a direct ByteBuffer) --------------------------------------
+class PinnedArena {
+ public:
+  ~PinnedArena() { release(p_, pinned_); }
+  uint8_t* data() { return p_; }
+  uint64_t size() const { return n_; }
+  void clear() { n_ = 0; }
+  void reserve(uint64_t cap) {
+    if (cap <= cap_) return;
+    uint64_t nc = cap_ ? cap_ : (1u << 20);
+    while (nc < cap) nc *= 2;
+    // Pinned when a CUDA device exists; plain heap otherwise so that pass-through mode (bytes already compressed
+    // upstream, no codec call) still works on a GPU-less box.  This is memory only: compute has no CPU fallback.
+    bool pinned = true;
+    uint8_t* q = (uint8_t*)b2s_host_alloc(nc);
+    if (!q) {
+      pinned = false;
+      q = (uint8_t*)malloc(nc);
+      if (!q) throw CodecException("out of host memory");
+    }
+    if (n_) memcpy(q, p_, n_);
+    release(p_, pinned_);
+    p_ = q;
+    pinned_ = pinned;
+    cap_ = nc;
+  }
+  void append(const uint8_t* b, uint64_t n) {
+    reserve(n_ + n);
+    memcpy(p_ + n_, b, n);
+    n_ += n;
+  }
+  void resize(uint64_t n) {
+    reserve(n);
+    n_ = n;
+  }
+
+ private:
+  static void release(uint8_t* p, bool pinned) {
+    if (!p) return;
+    if (pinned) b2s_host_free(p); else free(p);
+  }
+  uint8_t* p_ = nullptr;
+  uint64_t n_ = 0, cap_ = 0;
+  bool pinned_ = false;
+};
+
+static void mkdirs(const std::string& dir) {
+  std::string cur;
+  for (size_t i = 0; i < dir.size(); i++) {
+    cur.push_back(dir[i]);
+    if (dir[i] == '/' || i + 1 == dir.size()) {
+      if (cur.size() > 1 && mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST)
+        throw IOException("mkdir " + cur + ": " + strerror(errno));
+    }
+  }
+}
+
+// ---- S3ShuffleDispatcher (helper/S3ShuffleDispatcher.scala) -------------------------------------------------
+class S3ShuffleDispatcher {
+ public:
+  explicit S3ShuffleDispatcher(const std::string& conf_text) {
+    std::istringstream in(conf_text);
+    std::string line;
+    while (std::getline(in, line)) {
+      size_t eq = line.find('=');
+      if (eq == std::string::npos) continue;
+      conf_[line.substr(0, eq)] = line.substr(eq + 1);
+    }
+    appId = get("spark.app.id", "app-local");
+    std::string rd = get("spark.shuffle.s3.rootDir", "sparkS3shuffle/");  // :50
+    rootDir = (!rd.empty() && rd.back() == '/') ? rd : rd + "/";            // :51
+    rootIsLocal = rootDir.rfind("file:", 0) == 0;                            // :52
+    bufferSize = getInt("spark.shuffle.s3.bufferSize", 8 * 1024 * 1024);
+    maxBufferSizeTask = getInt("spark.shuffle.s3.maxBufferSizeTask", 128 * 1024 * 1024);
+    maxConcurrencyTask = getInt("spark.shuffle.s3.maxConcurrencyTask", 10);
+    cachePartitionLengths = getBool("spark.shuffle.s3.cachePartitionLengths", true);
+    cacheChecksums = getBool("spark.shuffle.s3.cacheChecksums", true);
+    cleanupShuffleFiles = getBool("spark.shuffle.s3.cleanup", true);
+    folderPrefixes = getInt("spark.shuffle.s3.folderPrefixes", 10);
+    alwaysCreateIndex = getBool("spark.shuffle.s3.alwaysCreateIndex", false);
+    forceBatchFetch = getBool("spark.shuffle.s3.forceBatchFetch", false);
+    checksumAlgorithm = get("spark.shuffle.checksum.algorithm", "ADLER32");  // Spark 3.5 default [U]
+    checksumEnabled = getBool("spark.shuffle.checksum.enabled", true);
+    shuffleCompress = getBool("spark.shuffle.compress", true);
+    codecName = get("spark.io.compression.codec", "lz4");
+    lz4BlockSize = (uint32_t)getSize("spark.io.compression.lz4.blockSize", 32 * 1024);
+    gpuEnabled = getBool("spark.shuffle.s3.gpu.enabled", true);  // additive key
+    if (!rootIsLocal && rootDir.find("://") != std::string::npos)
+      throw UnsupportedOperationException("only file:// roots are implemented by the host mirror: " + rootDir);
+  }
+
+  std::string localRoot() const { return rootIsLocal ? rootDir.substr(rootDir.find(':') + 1 + (rootDir.compare(5, 2, "//") == 0 ? 2 : 0)) : rootDir; }
+
+  // :120-144  ${rootDir}${mapId % folderPrefixes}/${appId}/${shuffleId}/${blockId.name}
+  std::string getPath(const BlockId& b) const {
+    std::ostringstream o;
+    o << localRoot() << (b.mapId % folderPrefixes) << "/" << appId << "/" << b.shuffleId << "/" << b.name();
+    return o.str();
+  }
+  std::string shuffleDir(int64_t prefix, int32_t shuffleId) const {
+    std::ostringstream o;
+    o << localRoot() << prefix << "/" << appId << "/" << shuffleId;
+    return o.str();
+  }
+  // :174-188 removeShuffle: every prefix folder
+  void removeShuffle(int32_t shuffleId) const {
+    for (int i = 0; i < folderPrefixes; i++) {
+      std::string dir = shuffleDir(i, shuffleId);
+      std::string cmd = "rm -rf '" + dir + "'";
+      if (system(cmd.c_str()) != 0) { /* like the reference: failures are only logged */ }
+    }
+  }
+  int codecId() const {
+    if (!shuffleCompress) return B2S_CODEC_NONE;
+    if (codecName == "lz4" || codecName == "org.apache.spark.io.LZ4CompressionCodec") return B2S_CODEC_LZ4BLOCK;
+    if (codecName == "snappy") return B2S_CODEC_SNAPPY_XERIAL;
+    if (codecName == "zstd") return B2S_CODEC_ZSTD;
+    throw UnsupportedOperationException("Unsupported compression codec: " + codecName);
+  }
+
+  std::string appId, rootDir, checksumAlgorithm, codecName;
+  bool rootIsLocal = false, cachePartitionLengths = true, cacheChecksums = true, cleanupShuffleFiles = true,
+       alwaysCreateIndex = false, forceBatchFetch = false, checksumEnabled = true, shuffleCompress = true,
+       gpuEnabled = true;
+  int bufferSize = 0, maxBufferSizeTask = 0, maxConcurrencyTask = 0, folderPrefixes = 10;
+  uint32_t lz4BlockSize = 32768;
+
+  // caches of S3ShuffleHelper (helper/S3ShuffleHelper.scala:15-16) live with the dispatcher instance here
+  std::mutex cacheMutex;
+  std::map<std::string, std::vector<int64_t>> cachedArrayLengths, cachedChecksums;
+
+ private:
+  std::string get(const std::string& k, const std::string& d) const {
+    auto it = conf_.find(k);
+    return it == conf_.end() ? d : it->second;
+  }
+  int getInt(const std::string& k, int d) const {
+    auto it = conf_.find(k);
+    return it == conf_.end() ? d : atoi(it->second.c_str());
+  }
+  long getSize(const std::string& k, long d) const {
+    auto it = conf_.find(k);
+    if (it == conf_.end()) return d;
+    char* end = nullptr;
+    long v = strtol(it->second.c_str(), &end, 10);
+    if (end && (*end == 'k' || *end == 'K')) v *= 1024;
+    if (end && (*end == 'm' || *end == 'M')) v *= 1024 * 1024;
+    return v;
+  }
+  bool getBool(const std::string& k, bool d) const {
+    auto it = conf_.find(k);
+    return it == conf_.end() ? d : (it->second == "true" || it->second == "1");
+  }
+  std::map<std::string, std::string> conf_;
+};
+
+// ---- S3ShuffleHelper (helper/S3ShuffleHelper.scala) ---------------------------------------------------------
+class S3ShuffleHelper {
+ public:
+  // :94-103 (+ "CRC32C", the case the Scala shim adds)
+  static uint32_t createChecksumAlgorithm(const std::string& algorithm) {
+    if (algorithm == "ADLER32") return B2S_CHECKSUM_ADLER32;
+    if (algorithm == "CRC32") return B2S_CHECKSUM_CRC32;
+    if (algorithm == "CRC32C") return B2S_CHECKSUM_CRC32C;
+    throw UnsupportedOperationException("Unsupported shuffle checksum algorithm: " + algorithm + ".");
+  }
+  static int64_t emptyChecksum(uint32_t alg) { return alg == B2S_CHECKSUM_ADLER32 ? 1 : 0; }
+
+  // :44-47  Array(0) ++ lengths.tail.scan(lengths.head)(_ + _)
+  static void writePartitionLengths(S3ShuffleDispatcher& d, int32_t shuffleId, int64_t mapId,
+                                    const std::vector<int64_t>& lengths) {
+    std::vector<int64_t> acc(lengths.size() + 1, 0);
+    for (size_t i = 0; i < lengths.size(); i++) acc[i + 1] = acc[i] + lengths[i];
+    writeArrayAsBlock(d, BlockId{BlockId::Index, shuffleId, mapId, 0, 0}, acc);
+  }
+  // :49-51
+  static void writeChecksum(S3ShuffleDispatcher& d, int32_t shuffleId, int64_t mapId,
+                            const std::vector<int64_t>& checksums) {
+    writeArrayAsBlock(d, BlockId{BlockId::Checksum, shuffleId, mapId, 0, 0}, checksums);
+  }
+  // :53-59 DataOutputStream.writeLong = big endian
+  static void writeArrayAsBlock(S3ShuffleDispatcher& d, const BlockId& b, const std::vector<int64_t>& a) {
+    std::string path = d.getPath(b);
+    mkdirs(path.substr(0, path.rfind('/')));
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    if (!f) throw IOException("cannot create " + path);
+    for (int64_t v : a) {
+      unsigned char be[8];
+      for (int k = 0; k < 8; k++) be[k] = (unsigned char)((uint64_t)v >> (56 - 8 * k));
+      f.write((const char*)be, 8);
+    }
+  }
+  // :105-121
+  static std::vector<int64_t> readBlockAsArray(S3ShuffleDispatcher& d, const BlockId& b) {
+    std::string path = d.getPath(b);
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw IOException("File does not exist: " + path);
+    std::streamoff len = f.tellg();
+    if (len % 8 != 0) throw SparkException("Unexpected file length when reading " + b.name());  // :112-114
+    f.seekg(0);
+    std::vector<int64_t> out((size_t)(len / 8));
+    for (auto& v : out) {
+      unsigned char be[8];
+      f.read((char*)be, 8);
+      uint64_t x = 0;
+      for (int k = 0; k < 8; k++) x = (x << 8) | be[k];
+      v = (int64_t)x;
+    }
+    return out;
+  }
+  // :67-92 cached readers
+  static std::vector<int64_t> getPartitionLengths(S3ShuffleDispatcher& d, int32_t shuffleId, int64_t mapId) {
+    BlockId b{BlockId::Index, shuffleId, mapId, 0, 0};
+    if (!d.cachePartitionLengths) return readBlockAsArray(d, b);
+    std::lock_guard<std::mutex> lk(d.cacheMutex);
+    auto it = d.cachedArrayLengths.find(b.name());
+    if (it == d.cachedArrayLengths.end()) it = d.cachedArrayLengths.emplace(b.name(), readBlockAsArray(d, b)).first;
+    return it->second;
+  }
+  static std::vector<int64_t> getChecksums(S3ShuffleDispatcher& d, int32_t shuffleId, int64_t mapId) {
+    BlockId b{BlockId::Checksum, shuffleId, mapId, 0, 0};
+    if (!d.cacheChecksums) return readBlockAsArray(d, b);
+    std::lock_guard<std::mutex> lk(d.cacheMutex);
+    auto it = d.cachedChecksums.find(b.name());
+    if (it == d.cachedChecksums.end()) it = d.cachedChecksums.emplace(b.name(), readBlockAsArray(d, b)).first;
+    return it->second;
+  }
+  static void purgeCachedDataForShuffle(S3ShuffleDispatcher& d, int32_t shuffleId) {  // :22-31
+    std::lock_guard<std::mutex> lk(d.cacheMutex);
+    std::string pre = "shuffle_" + std::to_string(shuffleId) + "_";
+    for (auto* m : {&d.cachedArrayLengths, &d.cachedChecksums})
+      for (auto it = m->begin(); it != m->end();) it = (it->first.rfind(pre, 0) == 0) ? m->erase(it) : std::next(it);
+  }
+};
+
+static void ensure_codec_runtime() {
+  int rc = b2s_init(0, 0, 0);
+  if (rc != 0) throw CodecException(std::string("b2s_init: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+}
+
+// ---- S3ShuffleMapOutputWriter (shuffle/S3ShuffleMapOutputWriter.scala) --------------------------------------
+class S3ShuffleMapOutputWriter {
+ public:
+  S3ShuffleMapOutputWriter(S3ShuffleDispatcher& d, int32_t shuffleId, int64_t mapId, int32_t numPartitions)
+      : d_(d), shuffleId_(shuffleId), mapId_(mapId), numPartitions_(numPartitions),
+        partitionLengths_((size_t)numPartitions, 0), partOff_((size_t)numPartitions, 0) {
+    gpu_ = d.gpuEnabled && d.codecId() != B2S_CODEC_NONE;
+  }
+
+  // :67-83
+  void getPartitionWriter(int32_t reducePartitionId) {
+    if (reducePartitionId <= lastPartitionWriterId_)
+      throw RuntimeException("Precondition: Expect a monotonically increasing reducePartitionId.");
+    if (reducePartitionId >= numPartitions_) throw RuntimeException("Precondition: Invalid partition id.");
+    lastPartitionWriterId_ = reducePartitionId;
+    current_ = reducePartitionId;
+    byteCount_ = 0;
+    streamOpen_ = true;
+    partOff_[(size_t)current_] = (int64_t)buf_.size();
+  }
+  // :182-188
+  void write(const uint8_t* b, uint64_t n) {
+    if (!streamOpen_) throw IOException("S3ShuffleOutputStream is already closed.");
+    buf_.append(b, n);
+    byteCount_ += (int64_t)n;
+  }
+  // :197-201
+  void closePartition() {
+    if (current_ < 0) return;
+    partitionLengths_[(size_t)current_] = byteCount_;
+    totalBytesWritten_ += byteCount_;
+    streamOpen_ = false;
+  }
+
+  // :91-118
+  std::vector<int64_t> commitAllPartitions(const int64_t* checksums_in) {
+    std::vector<int64_t> checksums((size_t)numPartitions_, 0);
+    const uint8_t* data = buf_.data();
+    uint64_t data_len = buf_.size();
+    if ((int64_t)data_len != totalBytesWritten_)
+      throw RuntimeException("S3ShuffleMapOutputWriter: Unexpected output length " + std::to_string(data_len) +
+                             ", expected: " + std::to_string(totalBytesWritten_) + ".");
+    const uint32_t alg = d_.checksumEnabled ? S3ShuffleHelper::createChecksumAlgorithm(d_.checksumAlgorithm) : 0;
+    if (gpu_) {
+      // SURVEY.md §3.2 option B: upstream wrote serialized *uncompressed* bytes; compress + checksum every
+      // non-empty partition in one batch.  Empty partitions stay 0 bytes long, as with Spark's own writers.
+      ensure_codec_runtime();
+      std::vector<uint64_t> off, len, doff, dlen, cks;
+      std::vector<int32_t> status, idx;
+      uint64_t bound = 0;
+      for (int32_t p = 0; p < numPartitions_; p++) {
+        if (partitionLengths_[(size_t)p] == 0) continue;
+        idx.push_back(p);
+        off.push_back((uint64_t)partOff_[(size_t)p]);
+        len.push_back((uint64_t)partitionLengths_[(size_t)p]);
+        bound += b2s_compress_bound((uint32_t)d_.codecId(), d_.lz4BlockSize, len.back());
+      }
+      const uint32_t n = (uint32_t)idx.size();
+      doff.resize(n); dlen.resize(n); cks.resize(n); status.resize(n);
+      out_.resize(bound);
+      uint64_t total = 0;
+      int rc = b2s_compress_packed((uint32_t)d_.codecId(), 0, d_.lz4BlockSize, alg, n, data, off.data(), len.data(),
+                                   out_.data(), bound, doff.data(), dlen.data(), &total, cks.data(), status.data());
+      if (rc != 0) throw CodecException(std::string("b2s_compress_packed: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+      for (uint32_t k = 0; k < n; k++)
+        if (status[k] != 0) throw IOException(std::string("compress failed: ") + b2s_strerror(status[k]));
+      std::fill(partitionLengths_.begin(), partitionLengths_.end(), 0);
+      for (int32_t p = 0; p < numPartitions_; p++) checksums[(size_t)p] = alg ? S3ShuffleHelper::emptyChecksum(alg) : 0;
+      for (uint32_t k = 0; k < n; k++) {
+        partitionLengths_[(size_t)idx[k]] = (int64_t)dlen[k];
+        checksums[(size_t)idx[k]] = (int64_t)cks[k];
+      }
+      data = out_.data();
+      data_len = total;
+    } else if (checksums_in) {
+      for (int32_t p = 0; p < numPartitions_; p++) checksums[(size_t)p] = checksums_in[p];
+    }
+    int64_t sum = 0;
+    for (int64_t v : partitionLengths_) sum += v;
+    if ((int64_t)data_len != sum)
+      throw RuntimeException("S3ShuffleMapOutputWriter: Unexpected output length " + std::to_string(data_len) +
+                             ", expected: " + std::to_string(sum) + ".");
+    if (lastPartitionWriterId_ >= 0) {  // the .data object exists as soon as a stream was opened (:43-49)
+      std::string path = d_.getPath(BlockId{BlockId::Data, shuffleId_, mapId_, 0, 0});
+      mkdirs(path.substr(0, path.rfind('/')));
+      std::ofstream f(path, std::ios::binary | std::ios::trunc);
+      if (!f) throw IOException("cannot create " + path);
+      f.write((const char*)data, (std::streamsize)data_len);
+    }
+    if (sum > 0 || d_.alwaysCreateIndex) {  // :111
+      S3ShuffleHelper::writePartitionLengths(d_, shuffleId_, mapId_, partitionLengths_);
+      if (d_.checksumEnabled) S3ShuffleHelper::writeChecksum(d_, shuffleId_, mapId_, checksums);
+    }
+    return partitionLengths_;
+  }
+  void abort() {  // :120-134
+    buf_.clear();
+    streamOpen_ = false;
+  }
+
+ private:
+  S3ShuffleDispatcher& d_;
+  int32_t shuffleId_;
+  int64_t mapId_;
+  int32_t numPartitions_;
+  std::vector<int64_t> partitionLengths_, partOff_;
+  int64_t totalBytesWritten_ = 0, byteCount_ = 0;
+  int32_t lastPartitionWriterId_ = -1, current_ = -1;
+  bool streamOpen_ = false, gpu_ = true;
+  PinnedArena buf_, out_;
+};
+
+// ---- S3ShuffleReader (storage/S3ShuffleReader.scala + block iterator/stream + checksum validation) ---------
+class S3ShuffleReader {
+ public:
+  struct Block {
+    BlockId id;
+    uint64_t srcOff = 0, srcLen = 0;    // in the fetched arena
+    uint64_t dstOff = 0, dstLen = 0;    // in the decoded arena
+  };
+  S3ShuffleReader(S3ShuffleDispatcher& d, int32_t shuffleId, std::vector<int64_t> mapIds, int32_t startPartition,
+                  int32_t endPartition, bool doBatchFetch)
+      : d_(d), shuffleId_(shuffleId), mapIds_(std::move(mapIds)), start_(startPartition), end_(endPartition),
+        batch_(doBatchFetch || d.forceBatchFetch) {}
+
+  // read(): storage/S3ShuffleReader.scala:77-110
+  void read() {
+    blocks_.clear();
+    remoteBytesRead_ = 0;
+    const bool verify = d_.checksumEnabled;
+    const uint32_t alg = verify ? S3ShuffleHelper::createChecksumAlgorithm(d_.checksumAlgorithm) : 0;
+    std::vector<uint64_t> off, len, sliceLen, sliceSum;
+    std::vector<uint32_t> sliceBase{0};
+    fetched_.clear();
+    // computeShuffleBlocks (:160-197) + S3ShuffleBlockIterator (storage/S3ShuffleBlockIterator.scala:36-43)
+    for (int64_t mapId : mapIds_) {
+      std::vector<int64_t> acc = S3ShuffleHelper::getPartitionLengths(d_, shuffleId_, mapId);
+      if ((int)acc.size() < end_ + 1) throw SparkException("index of map " + std::to_string(mapId) + " has too few partitions");
+      std::vector<int64_t> sums;
+      if (verify) sums = S3ShuffleHelper::getChecksums(d_, shuffleId_, mapId);
+      std::vector<std::pair<int32_t, int32_t>> ranges;
+      if (batch_ && end_ - start_ > 1) ranges.push_back({start_, end_});
+      else for (int32_t r = start_; r < end_; r++) ranges.push_back({r, r + 1});
+      std::ifstream f;
+      for (auto [rs, re] : ranges) {
+        const int64_t a = acc[(size_t)rs], b = acc[(size_t)re];
+        if (b - a == 0) continue;                    // filterNot(_._2.maxBytes == 0)  (:91)
+        remoteBytesRead_ += (uint64_t)(b - a);       // incRemoteBytesRead (:94)
+        Block blk;
+        blk.id = (re - rs > 1) ? BlockId{BlockId::ShuffleBatch, shuffleId_, mapId, rs, re}
+                               : BlockId{BlockId::Shuffle, shuffleId_, mapId, rs, re};
+        blk.srcOff = fetched_.size();
+        blk.srcLen = (uint64_t)(b - a);
+        // S3ShuffleBlockStream: positioned readFully of [acc(start), acc(end)) (storage/S3ShuffleBlockStream.scala:73-92)
+        if (!f.is_open()) {
+          std::string path = d_.getPath(BlockId{BlockId::Data, shuffleId_, mapId, 0, 0});
+          f.open(path, std::ios::binary);
+          if (!f) throw IOException("File does not exist: " + path);
+        }
+        fetched_.resize(blk.srcOff + blk.srcLen);
+        f.seekg(a);
+        f.read((char*)fetched_.data() + blk.srcOff, (std::streamsize)blk.srcLen);
+        if ((uint64_t)f.gcount() != blk.srcLen) throw IOException("short read on " + blk.id.name());
+        off.push_back(blk.srcOff);
+        len.push_back(blk.srcLen);
+        if (verify) {
+          for (int32_t r = rs; r < re; r++) {       // S3ChecksumValidationStream walks .index differences (:68-86)
+            sliceLen.push_back((uint64_t)(acc[(size_t)r + 1] - acc[(size_t)r]));
+            sliceSum.push_back((uint64_t)sums[(size_t)r]);
+          }
+          sliceBase.push_back((uint32_t)sliceLen.size());
+        }
+        blocks_.push_back(blk);
+      }
+    }
+    const uint32_t n = (uint32_t)blocks_.size();
+    if (!n) return;
+    ensure_codec_runtime();
+    const int codec = d_.codecId();
+    std::vector<uint64_t> doff(n), dlen(n);
+    std::vector<int32_t> status(n), bad(n);
+    uint64_t total = 0;
+    if (codec == B2S_CODEC_NONE) {
+      throw UnsupportedOperationException("spark.shuffle.compress=false is served by the stock reader path");
+    }
+    // size pass, then one batch: verify every slice over the compressed bytes, decode, verify block hashes
+    std::vector<const uint8_t*> ptr(n);
+    for (uint32_t k = 0; k < n; k++) ptr[k] = fetched_.data() + off[k];
+    int rc = b2s_decompressed_size_batch((uint32_t)codec, n, ptr.data(), len.data(), dlen.data(), status.data());
+    if (rc != 0) throw CodecException(std::string("b2s_decompressed_size_batch: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+    uint64_t cap = 0;
+    for (uint32_t k = 0; k < n; k++) cap += dlen[k];
+    decoded_.resize(cap ? cap : 1);
+    rc = b2s_decompress_packed((uint32_t)codec, alg, n, fetched_.data(), off.data(), len.data(),
+                               verify ? sliceBase.data() : nullptr, verify ? sliceLen.data() : nullptr,
+                               verify ? sliceSum.data() : nullptr, decoded_.data(), cap ? cap : 1, doff.data(),
+                               dlen.data(), &total, status.data(), bad.data());
+    if (rc != 0) throw CodecException(std::string("b2s_decompress_packed: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+    for (uint32_t k = 0; k < n; k++) {
+      if (status[k] == B2S_E_CHECKSUM)  // storage/S3ChecksumValidationStream.scala:72-74
+        throw SparkException("Invalid checksum detected for " + blocks_[k].id.name());
+      if (status[k] == B2S_E_CORRUPT) throw IOException("Stream is corrupted");
+      if (status[k] != 0) throw IOException(std::string("decompress failed: ") + b2s_strerror(status[k]));
+      blocks_[k].dstOff = doff[k];
+      blocks_[k].dstLen = dlen[k];
+    }
+  }
+  const std::vector<Block>& blocks() const { return blocks_; }
+  const uint8_t* decoded() { return decoded_.data(); }
+  uint64_t remoteBytesRead() const { return remoteBytesRead_; }
+
+ private:
+  S3ShuffleDispatcher& d_;
+  int32_t shuffleId_;
+  std::vector<int64_t> mapIds_;
+  int32_t start_, end_;
+  bool batch_;
+  std::vector<Block> blocks_;
+  PinnedArena fetched_, decoded_;
+  uint64_t remoteBytesRead_ = 0;
+};
+
+}  // namespace host
+}  // namespace b2s
+
+// =====================================================================================================
+// C wrapper
+// =====================================================================================================
+using namespace b2s::host;
+
+static thread_local std::string t_err;
+struct b2sh_dispatcher { std::unique_ptr<S3ShuffleDispatcher> d; };
+struct b2sh_writer { std::unique_ptr<S3ShuffleMapOutputWriter> w; int32_t n; };
+struct b2sh_reader { std::unique_ptr<S3ShuffleReader> r; };
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    t_err.clear();
+    return B2SH_OK;
+  } catch (const RuntimeException& e) { t_err = e.what(); return B2SH_E_RUNTIME;
+  } catch (const IOException& e) { t_err = e.what(); return B2SH_E_IO;
+  } catch (const SparkException& e) { t_err = e.what(); return B2SH_E_SPARK;
+  } catch (const UnsupportedOperationException& e) { t_err = e.what(); return B2SH_E_UNSUPPORTED;
+  } catch (const CodecException& e) { t_err = e.what(); return B2SH_E_CODEC;
+  } catch (const std::exception& e) { t_err = e.what(); return B2SH_E_RUNTIME; }
+}
+
+extern "C" {
+
+const char* b2sh_last_error(void) { return t_err.c_str(); }
+
+int b2sh_dispatcher_create(const char* conf, b2sh_dispatcher** out) {
+  return guarded([&] { *out = new b2sh_dispatcher{std::make_unique<S3ShuffleDispatcher>(conf ? conf : "")}; });
+}
+void b2sh_dispatcher_destroy(b2sh_dispatcher* d) { delete d; }
+int b2sh_dispatcher_get_path(b2sh_dispatcher* d, int kind, int32_t shuffle_id, int64_t map_id, char* buf, uint32_t cap) {
+  return guarded([&] {
+    BlockId::Kind k = kind == 0 ? BlockId::Data : kind == 1 ? BlockId::Index : BlockId::Checksum;
+    std::string p = d->d->getPath(BlockId{k, shuffle_id, map_id, 0, 0});
+    if (p.size() + 1 > cap) throw RuntimeException("path buffer too small");
+    memcpy(buf, p.c_str(), p.size() + 1);
+  });
+}
+int b2sh_dispatcher_remove_shuffle(b2sh_dispatcher* d, int32_t shuffle_id) {
+  return guarded([&] {
+    d->d->removeShuffle(shuffle_id);
+    S3ShuffleHelper::purgeCachedDataForShuffle(*d->d, shuffle_id);
+  });
+}
+int b2sh_helper_checksum_algorithm(const char* name) {
+  int id = 0;
+  int rc = guarded([&] { id = (int)S3ShuffleHelper::createChecksumAlgorithm(name ? name : ""); });
+  return rc ? rc : id;
+}
+static int copy_out(const std::vector<int64_t>& v, int64_t* out, uint32_t cap, uint32_t* count) {
+  *count = (uint32_t)v.size();
+  if (v.size() > cap) throw RuntimeException("output array too small");
+  memcpy(out, v.data(), v.size() * 8);
+  return 0;
+}
+int b2sh_helper_get_partition_lengths(b2sh_dispatcher* d, int32_t s, int64_t m, int64_t* out, uint32_t cap, uint32_t* count) {
+  return guarded([&] { copy_out(S3ShuffleHelper::getPartitionLengths(*d->d, s, m), out, cap, count); });
+}
+int b2sh_helper_get_checksums(b2sh_dispatcher* d, int32_t s, int64_t m, int64_t* out, uint32_t cap, uint32_t* count) {
+  return guarded([&] { copy_out(S3ShuffleHelper::getChecksums(*d->d, s, m), out, cap, count); });
+}
+
+int b2sh_writer_create(b2sh_dispatcher* d, int32_t shuffle_id, int64_t map_id, int32_t num_partitions, b2sh_writer** out) {
+  return guarded([&] {
+    *out = new b2sh_writer{std::make_unique<S3ShuffleMapOutputWriter>(*d->d, shuffle_id, map_id, num_partitions), num_partitions};
+  });
+}
+int b2sh_writer_open_partition(b2sh_writer* w, int32_t reduce_id) { return guarded([&] { w->w->getPartitionWriter(reduce_id); }); }
+int b2sh_writer_write(b2sh_writer* w, const uint8_t* bytes, uint64_t n) { return guarded([&] { w->w->write(bytes, n); }); }
+int b2sh_writer_close_partition(b2sh_writer* w) { return guarded([&] { w->w->closePartition(); }); }
+int b2sh_writer_commit_all_partitions(b2sh_writer* w, const int64_t* checksums_in, int64_t* partition_lengths_out) {
+  return guarded([&] {
+    std::vector<int64_t> l = w->w->commitAllPartitions(checksums_in);
+    memcpy(partition_lengths_out, l.data(), l.size() * 8);
+  });
+}
+int b2sh_writer_abort(b2sh_writer* w) { return guarded([&] { w->w->abort(); }); }
+void b2sh_writer_destroy(b2sh_writer* w) { delete w; }
+
+int b2sh_reader_create(b2sh_dispatcher* d, int32_t shuffle_id, const int64_t* map_ids, uint32_t n_maps, int32_t start_partition,
+                       int32_t end_partition, int do_batch_fetch, b2sh_reader** out) {
+  return guarded([&] {
+    *out = new b2sh_reader{std::make_unique<S3ShuffleReader>(*d->d, shuffle_id, std::vector<int64_t>(map_ids, map_ids + n_maps),
+                                                             start_partition, end_partition, do_batch_fetch != 0)};
+  });
+}
+int b2sh_reader_read(b2sh_reader* r, uint32_t* n_blocks) {
+  return guarded([&] {
+    r->r->read();
+    *n_blocks = (uint32_t)r->r->blocks().size();
+  });
+}
+int b2sh_reader_block(b2sh_reader* r, uint32_t k, int64_t* map_id, int32_t* start_reduce, int32_t* end_reduce,
+                      const uint8_t** data, uint64_t* len) {
+  return guarded([&] {
+    if (k >= r->r->blocks().size()) throw RuntimeException("block index out of range");
+    const auto& b = r->r->blocks()[k];
+    *map_id = b.id.mapId;
+    *start_reduce = b.id.reduceId;
+    *end_reduce = b.id.kind == BlockId::ShuffleBatch ? b.id.endReduceId : b.id.reduceId + 1;
+    *data = r->r->decoded() + b.dstOff;
+    *len = b.dstLen;
+  });
+}
+uint64_t b2sh_reader_remote_bytes_read(b2sh_reader* r) { return r->r->remoteBytesRead(); }
+void b2sh_reader_destroy(b2sh_reader* r) { delete r; }
+
+}  // extern "C"
