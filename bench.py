@@ -161,28 +161,15 @@ def main():
 
     # ------------------------------------------------------------------ B200 arm
     import torch
-    import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import spark_s3_shuffle_b200 as pkg
 
+    rk = pkg.ranks.Ranks(backend="nccl", device=torch.device("cuda", local_rank))  # barrier + max-over-ranks only
     c = pkg.capi
     c.init(1 << local_rank)
     L = c.load()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier, max_over_ranks = rk.barrier, rk.max_over_ranks
 
     cmp_cap = int(c.compress_bound(c.CODEC_LZ4BLOCK, LZ4_BLOCK, block_bytes)) * n
     d_src, d_cmp, d_out = c.dev_alloc(total), c.dev_alloc(cmp_cap), c.dev_alloc(total)
@@ -306,8 +293,7 @@ def main():
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    rk.close()
     return 0
 
 

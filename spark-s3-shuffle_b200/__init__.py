@@ -10,7 +10,7 @@ compute entry point returns ``B2S_E_CUDA`` when no GPU is usable.
 import importlib
 import os
 
-__all__ = ["capi", "host", "lib_path", "build"]
+__all__ = ["capi", "host", "ranks", "lib_path", "build"]
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -25,6 +25,6 @@ def build(force=False, verbose=False):
 
 
 def __getattr__(name):
-    if name in ("capi", "host", "_build"):
+    if name in ("capi", "host", "ranks", "_build"):
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)
