@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import spark_s3_shuffle_b200 as pkg
-from tests.shuffle_model import decode_pairs, encode_pairs, oracle_read_partition
+from shuffle_model import decode_pairs, encode_pairs, oracle_read_partition
 
 pytestmark = pytest.mark.gpu
 host = pkg.host
