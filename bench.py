@@ -178,7 +178,8 @@ def main():
     ln = np.full(n, block_bytes, dtype=np.uint64)
     sb = np.arange(n + 1, dtype=np.uint32)
 
-    kt = {"write_kernel_ms": [], "read_kernel_ms": [], "compress_ms": [], "decompress_ms": []}
+    kt = {"write_kernel_ms": [], "read_kernel_ms": [], "compress_ms": [], "decompress_ms": [], "match_ms": [],
+          "match_launches": []}
 
     def step_device(record):
         w = c.compress_dev(c.CODEC_LZ4BLOCK, d_src, off, ln, d_cmp, cmp_cap, LZ4_BLOCK, c.CHECKSUM_CRC32C)
@@ -188,6 +189,7 @@ def main():
         tr = c.last_timing()
         if record:
             kt["write_kernel_ms"].append(tw["kernel_ms"]); kt["compress_ms"].append(tw["top_kernel_ms"])
+            kt["match_ms"].append(tw["dominant_ms"]); kt["match_launches"].append(tw["dominant_launches"])
             kt["read_kernel_ms"].append(tr["kernel_ms"]); kt["decompress_ms"].append(tr["top_kernel_ms"])
         return w, r
 
@@ -214,14 +216,23 @@ def main():
     value = world * total / (elapsed / steps) / 1e9
 
     comp_ms = statistics.mean(kt["compress_ms"])
+    match_ms = statistics.mean(kt["match_ms"])
+    match_launches = max(1, int(statistics.mean(kt["match_launches"])))
     peak, peak_src = measured_peak()
-    alg_bytes = (1.0 + ratio) * total                      # K3 reads U, writes C
-    achieved = alg_bytes / (comp_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "lz4_compress_kernel<12>", "achieved": round(achieved, 2), "peak": peak,
+    # dominant kernel = lz4_match_kernel (phase A of the compressor).  Its algorithmic traffic per launch: read the
+    # chunk's U bytes once, write the per-position match table (off u16 + ml8 u8 = 3 B per input byte) — DESIGN.md §4.
+    alg_bytes = 4.0 * total / match_launches
+    achieved = alg_bytes / (match_ms / match_launches * 1e-3) / 1e9
+    step_alg = (1.0 + ratio) * total                       # compress step reads U, writes C
+    roofline = {"bound": "hbm", "kernel": "lz4_match_kernel<12>", "achieved": round(achieved, 2), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(comp_ms, 4),
+                "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(match_ms / match_launches, 4),
+                "launches_per_step": match_launches,
+                "compress_step": {"kernels": "match + parse + scan + emit", "algorithmic_bytes": int(step_alg),
+                                  "ms": round(comp_ms, 3), "achieved": round(step_alg / (comp_ms * 1e-3) / 1e9, 2),
+                                  "frac": round(step_alg / (comp_ms * 1e-3) / 1e9 / peak, 5)},
                 "note": "LZ codec kernels are issue/latency bound byte-stream work; frac is honest HBM utilisation"}
-    kernels = {"compress_ms": round(comp_ms, 3), "decompress_ms": round(statistics.mean(kt["decompress_ms"]), 3),
+    kernels = {"compress_ms": round(comp_ms, 3), "match_ms": round(match_ms, 3), "decompress_ms": round(statistics.mean(kt["decompress_ms"]), 3),
                "write_pass_kernels_ms": round(statistics.mean(kt["write_kernel_ms"]), 3),
                "read_pass_kernels_ms": round(statistics.mean(kt["read_kernel_ms"]), 3),
                "compress_GBps_uncompressed": round(total / comp_ms / 1e6, 2),

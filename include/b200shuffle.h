@@ -143,10 +143,12 @@ typedef struct b2s_timing {
   double total_ms;        /* host wall time of the last call on this thread */
   double h2d_ms, d2h_ms;  /* CUDA-event time of the copies (0 for _dev calls) */
   double kernel_ms;       /* CUDA-event time from first to last kernel of the call */
-  double top_kernel_ms;   /* CUDA-event time of the dominant kernel (lz4 compress / decompress / checksum) */
+  double top_kernel_ms;   /* CUDA-event time of the codec step (lz4 match+parse+emit / decompress / checksum) */
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t kernel_launches; /* kernels launched by the call */
   uint64_t src_bytes, dst_bytes;
+  double dominant_ms;       /* CUDA-event time of the single dominant kernel (lz4_match_kernel / lz4 decode), summed over its launches */
+  uint64_t dominant_launches;
 } b2s_timing;
 int b2s_last_timing(b2s_timing* out);
 uint64_t b2s_total_kernel_launches(void); /* process-wide counter since b2s_init */

@@ -223,63 +223,58 @@ last_literals:
 }
 
 /*
- * CPU model of the GPU LZ4 compressor (spark-s3-shuffle_b200/csrc/lz4.cu) — its executable
- * specification: the kernel's output is bit-identical.  "Window-batched greedy": the 32 positions of a window are
- * looked up against the hash table as it stood before the window (so a match never references its own window
- * through the table; byte runs are caught by an explicit offset-1 candidate instead), the parse then walks the window greedily (lowest matching position at or after the parse
- * cursor, full forward extension), and finally every position of the window is inserted (highest position wins a
- * slot).  A match that overshoots the window moves the next window to its end.  u16 table, zero-initialised.
+ * CPU model of the GPU compressor — the kernels' executable specification, bit-identical output.
+ * Three phases, mirroring the three kernels:
+ *  A  match finding, parse-independent: the block is cut into FIXED windows of 32 positions.  Every position
+ *     p <= mflimit of a window looks its 4 bytes up in a u16 hash table holding the state *before* the window
+ *     (zero-initialised, so position 0 is a legal candidate); a byte run (the 4 bytes at p-1 equal those at p) uses
+ *     the offset-1 candidate instead.  A verified candidate yields off[p] = p - cand, else 0.  Then all positions
+ *     of the window are inserted (highest position wins a slot).
+ *  B  greedy parse over off[]: the lowest p >= cursor with off[p] != 0 starts a match, extended forward to
+ *     matchlimit; the cursor jumps to its end.
+ *  C  LZ4 sequence emission.
  */
 int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap, int hash_log) {
   enum { W = 32 };
   if (n > 65536 || hash_log > 16 || hash_log < 4) return 0;
   uint16_t* table = (uint16_t*)calloc((size_t)1 << hash_log, sizeof(uint16_t));
-  int op = 0, anchor = 0, pos = 0;
+  uint16_t* off = (uint16_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(uint16_t));
+  int op = 0, anchor = 0;
   if (n >= LZ4_MFLIMIT + 1) {
     const int mflimit = n - LZ4_MFLIMIT;
     const int matchlimit = n - LZ4_LASTLITERALS;
-    while (pos <= mflimit) {
-      uint32_t hs[W];
-      int cand[W], ok[W];
-      for (int r = 0; r < W; r++) {
-        int p = pos + r;
-        hs[r] = 0xffffffffu;
-        ok[r] = 0;
-        if (p > mflimit) continue;
-        uint32_t v = rd32(src + p);
-        uint32_t h = lz4_hash(v, hash_log);
-        hs[r] = h;
-        int c = table[h];
-        if (p > 0 && rd32(src + p - 1) == v) { /* run of one byte value: offset-1 candidate, like a sequential table */
-          ok[r] = 1;
-          cand[r] = p - 1;
-        } else if (c < p && rd32(src + c) == v) {
-          ok[r] = 1;
-          cand[r] = c;
-        }
+    for (int pos = 0; pos <= mflimit; pos += W) { /* phase A */
+      const int last = pos + W - 1 < mflimit ? pos + W - 1 : mflimit;
+      for (int p = pos; p <= last; p++) {
+        const uint32_t v = rd32(src + p);
+        const int c = table[lz4_hash(v, hash_log)];
+        if (p > 0 && rd32(src + p - 1) == v) off[p] = 1;
+        else if (c < p && rd32(src + c) == v) off[p] = (uint16_t)(p - c);
       }
-      int s = 0;
-      while (s < W) {
-        int r = s;
-        while (r < W && !ok[r]) r++;
-        if (r >= W) break;
-        int m = pos + r, c = cand[r], mlen = LZ4_MINMATCH;
-        while (m + mlen < matchlimit && src[m + mlen] == src[c + mlen]) mlen++;
-        op = lz4_emit_seq(src, anchor, m - anchor, m - c, mlen, dst, op, cap);
-        if (op < 0) {
-          free(table);
-          return 0;
-        }
-        anchor = m + mlen;
-        s = r + mlen;
+      for (int p = pos; p <= last; p++) table[lz4_hash(rd32(src + p), hash_log)] = (uint16_t)p;
+    }
+    int p = 0; /* phase B + C */
+    while (p <= mflimit) {
+      if (!off[p]) {
+        p++;
+        continue;
       }
-      for (int r = 0; r < W; r++)
-        if (hs[r] != 0xffffffffu) table[hs[r]] = (uint16_t)(pos + r);
-      pos += s > W ? s : W;
+      const int c = p - off[p];
+      int mlen = LZ4_MINMATCH;
+      while (p + mlen < matchlimit && src[p + mlen] == src[c + mlen]) mlen++;
+      op = lz4_emit_seq(src, anchor, p - anchor, off[p], mlen, dst, op, cap);
+      if (op < 0) {
+        free(table);
+        free(off);
+        return 0;
+      }
+      p += mlen;
+      anchor = p;
     }
   }
   op = lz4_emit_seq(src, anchor, n - anchor, 0, 0, dst, op, cap);
   free(table);
+  free(off);
   return op < 0 ? 0 : op;
 }
 

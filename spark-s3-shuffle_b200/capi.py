@@ -25,7 +25,7 @@ class Timing(C.Structure):
     _fields_ = [
         ("total_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("kernel_ms", C.c_double),
         ("top_kernel_ms", C.c_double), ("h2d_bytes", _u64), ("d2h_bytes", _u64), ("kernel_launches", _u64),
-        ("src_bytes", _u64), ("dst_bytes", _u64),
+        ("src_bytes", _u64), ("dst_bytes", _u64), ("dominant_ms", C.c_double), ("dominant_launches", _u64),
     ]
 
     def as_dict(self):

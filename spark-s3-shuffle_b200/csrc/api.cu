@@ -46,6 +46,8 @@ constexpr int NSLOT = 3;
 constexpr uint64_t kChunkBytes = 64ull << 20;
 constexpr uint32_t kChunkStreams = 1u << 18;
 constexpr uint32_t kXxhSeed = 0x9747b28cu;
+uint32_t g_lz4_chunk_blocks = 32768;
+int g_lz4d_legacy = 0;  // B2S_LZ4D_LEGACY=1: single-kernel tile decoder for every block size (A/B comparisons)  // codec blocks per match/parse/emit pass (bounds the workspace); B2S_LZ4_CHUNK_BLOCKS
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -116,12 +118,29 @@ struct Carver {
 
 struct Slot {
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;                               // side stream: match kernels of chunk k+1 overlap parse/emit of chunk k
+  cudaEvent_t ev_fork = nullptr, ev_match[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;              // readback milestones
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;            // kernel region
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;            // dominant kernel
   cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;  // copies
   DevBuf meta, scratch, desc, src, dst;
   PinBuf hmeta;
+  // per-launch event pairs around the dominant kernel of a call (grow-only pool; `used` pairs are valid)
+  std::vector<cudaEvent_t> ev_dom;
+  size_t dom_used = 0;
+  int dom_pair(cudaEvent_t* a, cudaEvent_t* b) {
+    if (dom_used * 2 + 2 > ev_dom.size()) {
+      cudaEvent_t x = nullptr, y = nullptr;
+      if (cudaEventCreate(&x) != cudaSuccess || cudaEventCreate(&y) != cudaSuccess) return -1;
+      ev_dom.push_back(x);
+      ev_dom.push_back(y);
+    }
+    *a = ev_dom[dom_used * 2];
+    *b = ev_dom[dom_used * 2 + 1];
+    dom_used++;
+    return 0;
+  }
 };
 
 struct Device {
@@ -223,7 +242,7 @@ struct CompressDevMeta {
   uint32_t* blk_base;
   uint64_t *dst_off, *dst_len, *cks, *total;
   int32_t* status;
-  uint32_t *csize, *hash;
+  uint32_t *csize, *hash, *nseq;
   uint64_t *sizes, *work_base, *ws;
   unsigned int* counter;
 };
@@ -231,12 +250,14 @@ struct CompressDevMeta {
 int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t bs, uint32_t alg, CompressJob& J,
                      const uint8_t* d_src, uint8_t* d_dst, uint64_t dst_cap, CompressDevMeta& M, uint64_t* launches) {
   const uint32_t n = J.n, nb = J.nb;
+  const uint32_t chunk = std::min<uint32_t>(nb ? nb : 1, g_lz4_chunk_blocks);
   size_t ws_elems = std::max(scan_ws_elems(nb + 1), checksum_ws_elems(n)) + 4;
-  size_t need = J.up_bytes + J.down_bytes + align_up((size_t)nb * 4, 16) * 2 + align_up(((size_t)nb + 1) * 8, 16) +
+  size_t need = J.up_bytes + J.down_bytes + align_up((size_t)nb * 4, 16) * 3 + align_up(((size_t)nb + 1) * 8, 16) +
                 align_up(((size_t)n + 1) * 8, 16) + ws_elems * 8 + 256;
   int rc = S.meta.ensure(need);
   if (rc) return rc;
-  rc = S.scratch.ensure((size_t)nb * bs + 64);
+  const size_t ws_bytes = align_up(lz4_compress_ws_bytes(chunk, bs), 256);
+  rc = S.scratch.ensure(ws_bytes * (nb > chunk ? 2 : 1));
   if (rc) return rc;
   Carver dc(S.meta.p);
   J.d_up = (uint8_t*)dc.take<uint64_t>(0);
@@ -252,6 +273,7 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
   M.status = dc.take<int32_t>(n);
   M.csize = dc.take<uint32_t>(nb);
   M.hash = dc.take<uint32_t>(nb);
+  M.nseq = dc.take<uint32_t>(nb);
   M.sizes = dc.take<uint64_t>((size_t)nb + 1);
   M.work_base = dc.take<uint64_t>((size_t)n + 1);
   M.ws = dc.take<uint64_t>(ws_elems);
@@ -271,12 +293,31 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
   CU(cudaEventRecord(S.ev_k0, st));
   launch_xxh32_encode(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, kXxhSeed, M.hash, st, launches);
   CU(cudaEventRecord(S.ev_t0, st));
-  launch_lz4_compress(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, (uint8_t*)S.scratch.p, M.csize, M.sizes,
-                      M.counter, st, launches);
+  CU(cudaMemsetAsync(M.total, 0, 16, st));
+  // Chunks of `chunk` codec blocks.  The match kernel (issue bound, shared-memory limited) of chunk k+1 runs on the
+  // side stream while parse (latency bound, one thread per block), scan and emit of chunk k run on the main stream;
+  // the two workspaces alternate.
+  CU(cudaEventRecord(S.ev_fork, st));
+  CU(cudaStreamWaitEvent(S.st2, S.ev_fork, 0));
+  uint32_t k = 0;
+  for (uint32_t b0 = 0; b0 < nb; b0 += chunk, k++) {
+    const uint32_t m = std::min<uint32_t>(chunk, nb - b0);
+    const int par = (int)(k & 1);
+    uint8_t* ws = (uint8_t*)S.scratch.p + (size_t)par * ws_bytes;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    S.dom_pair(&e0, &e1);
+    if (k >= 2) CU(cudaStreamWaitEvent(S.st2, S.ev_free[par], 0));  // emit of chunk k-2 has released this workspace
+    launch_lz4_match(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, ws, M.counter + par, S.st2, launches, e0,
+                     e1);
+    CU(cudaEventRecord(S.ev_match[par], S.st2));
+    CU(cudaStreamWaitEvent(st, S.ev_match[par], 0));
+    launch_lz4_parse_emit(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, ws, M.nseq, M.csize, M.hash, M.sizes,
+                          M.total, M.ws, d_dst, dst_cap, st, launches);
+    CU(cudaEventRecord(S.ev_free[par], st));
+  }
   CU(cudaEventRecord(S.ev_t1, st));
-  launch_exclusive_scan_u64(M.sizes, nb, M.total, M.ws, st, launches);
-  launch_lz4block_pack(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, (const uint8_t*)S.scratch.p, M.csize,
-                       M.hash, M.sizes, M.total, d_dst, dst_cap, M.dst_off, M.dst_len, M.status, st, launches);
+  launch_lz4block_stream_meta(M.blk_base, n, nb, bs, M.sizes, M.total, d_dst, dst_cap, M.dst_off, M.dst_len, M.status,
+                              st, launches);
   if (alg != B2S_CHECKSUM_NONE) {
     uint32_t shift = pick_tile_shift(dst_cap < (uint64_t)nb * bs ? dst_cap : (uint64_t)nb * bs);
     launch_checksum(tabs, alg, d_dst, M.dst_off, M.dst_len, n, shift, M.work_base, M.ws, M.cks, st, launches);
@@ -386,12 +427,12 @@ int decompress_enqueue_a(Slot& S, const ChecksumTables& tabs, uint32_t alg, Deco
                     J.cks_got, st, launches);
     launch_checksum_compare(J.cks_got, J.slice_sum, J.slice_owner, J.slice_base, s, J.status, J.bad, st, launches);
   }
-  launch_lz4block_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.status, st, launches);
+  launch_lz4block_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.totals + 2, J.status, st, launches);
   // dst_off = exclusive scan(olen) ; blk_base = exclusive scan(nblk) (in place)
   CU(cudaMemcpyAsync(J.dst_off, J.olen, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
   launch_exclusive_scan_u64(J.dst_off, n, J.totals + 1, J.ws, st, launches);
   launch_exclusive_scan_u64(J.nblk, n, J.totals + 0, J.ws, st, launches);
-  CU(cudaMemcpyAsync(J.h_totals, J.totals, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(J.h_totals, J.totals, 32, cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(S.ev_a, st));
   CU(cudaGetLastError());
   return 0;
@@ -411,7 +452,26 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
   launch_lz4block_fill(d_src, J.src_off, J.src_len, J.n, J.nblk, J.dst_off, J.olen, dst_cap, J.status, desc, st,
                        launches);
   CU(cudaEventRecord(S.ev_t0, st));
-  launch_lz4_decompress(desc, (uint32_t)J.nb, d_src, d_dst, J.status, J.counter, st, launches);
+  const uint64_t max_olen = J.h_totals[2], max_clen = J.h_totals[3];
+  if (J.nb && max_olen <= 65536 && max_clen < 65536 && !g_lz4d_legacy) {
+    // tokens (thread per block) + copy (lane per sequence), in chunks that bound the record workspace
+    const uint32_t nb = (uint32_t)J.nb;
+    const uint32_t chunk = std::min<uint32_t>(nb, g_lz4_chunk_blocks);
+    rc = S.scratch.ensure(lz4_decode_ws_bytes(chunk, (uint32_t)max_olen) + align_up((size_t)nb * 4, 256));
+    if (rc) return rc;
+    uint32_t* nrec = (uint32_t*)S.scratch.p;
+    uint8_t* ws = (uint8_t*)S.scratch.p + align_up((size_t)nb * 4, 256);
+    for (uint32_t b0 = 0; b0 < nb; b0 += chunk) {
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      S.dom_pair(&e0, &e1);
+      CU(cudaEventRecord(e0, st));
+      launch_lz4_decode_chunk(desc, b0, std::min<uint32_t>(chunk, nb - b0), (uint32_t)max_olen, d_src, d_dst, ws, nrec,
+                              J.status, st, launches);
+      CU(cudaEventRecord(e1, st));
+    }
+  } else {
+    launch_lz4_decompress(desc, (uint32_t)J.nb, d_src, d_dst, J.status, J.counter, st, launches);
+  }
   CU(cudaEventRecord(S.ev_t1, st));
   launch_xxh32_verify(desc, (uint32_t)J.nb, d_dst, kXxhSeed, 0x0FFFFFFFu, J.status, st, launches);
   CU(cudaEventRecord(S.ev_k1, st));
@@ -432,6 +492,11 @@ int get_device(uint32_t dev_index, Device** out) {
 void add_timing(Slot& S, bool copies) {
   t_timing.kernel_ms += ms_between(S.ev_k0, S.ev_k1);
   t_timing.top_kernel_ms += ms_between(S.ev_t0, S.ev_t1);
+  for (size_t k = 0; k < S.dom_used; k++) {
+    t_timing.dominant_ms += ms_between(S.ev_dom[2 * k], S.ev_dom[2 * k + 1]);
+    t_timing.dominant_launches++;
+  }
+  S.dom_used = 0;
   if (copies) t_timing.h2d_ms += ms_between(S.ev_h0, S.ev_h1);  // d2h is added once the payload copy has run
 }
 
@@ -517,6 +582,8 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
     return fail(B2S_E_CUDA, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
   g_lz4_hlog = env_int("B2S_LZ4_HLOG", g_lz4_hlog);
   g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
+  g_lz4_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4_CHUNK_BLOCKS", (int)g_lz4_chunk_blocks));
+  g_lz4d_legacy = env_int("B2S_LZ4D_LEGACY", 0);
   Context* C = new Context();
   for (int d = 0; d < count && d < 32; d++) {
     if (gpu_mask && !(gpu_mask & (1u << d))) continue;
@@ -526,6 +593,9 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
     for (int k = 0; k < NSLOT; k++) {
       Slot& S = D->slot[k];
       CU(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&S.st2, cudaStreamNonBlocking));
+      cudaEvent_t* evs2[] = {&S.ev_fork, &S.ev_match[0], &S.ev_match[1], &S.ev_free[0], &S.ev_free[1]};
+      for (auto p : evs2) CU(cudaEventCreateWithFlags(p, cudaEventDisableTiming));
       cudaEvent_t* evs[] = {&S.ev_a, &S.ev_b, &S.ev_k0, &S.ev_k1, &S.ev_t0, &S.ev_t1, &S.ev_h0, &S.ev_h1, &S.ev_d0, &S.ev_d1};
       for (auto p : evs) CU(cudaEventCreate(p));
     }
@@ -557,6 +627,12 @@ void b2s_shutdown(void) {
       cudaEvent_t evs[] = {S.ev_a, S.ev_b, S.ev_k0, S.ev_k1, S.ev_t0, S.ev_t1, S.ev_h0, S.ev_h1, S.ev_d0, S.ev_d1};
       for (auto ev : evs)
         if (ev) cudaEventDestroy(ev);
+      for (auto ev : S.ev_dom) cudaEventDestroy(ev);
+      S.ev_dom.clear();
+      cudaEvent_t evs2[] = {S.ev_fork, S.ev_match[0], S.ev_match[1], S.ev_free[0], S.ev_free[1]};
+      for (auto ev : evs2)
+        if (ev) cudaEventDestroy(ev);
+      if (S.st2) cudaStreamDestroy(S.st2);
       if (S.st) cudaStreamDestroy(S.st);
     }
     checksum_tables_destroy(&D->tabs);

@@ -11,8 +11,10 @@ namespace b2s {
 // in-place exclusive prefix sum over d_v[0..n); d_total (device, 1 element) receives the grand total.
 // d_ws must hold scan_ws_elems(n) uint64.
 size_t scan_ws_elems(size_t n);
+// d_base (optional, device): offset added to every result and to the total; d_total may alias d_base, which chains
+// the scans of consecutive chunks into one running prefix.
 void launch_exclusive_scan_u64(uint64_t* d_v, size_t n, uint64_t* d_total, uint64_t* d_ws, cudaStream_t st,
-                               uint64_t* launches);
+                               uint64_t* launches, const uint64_t* d_base = nullptr);
 
 // ---------------- checksum.cu (K1) ----------------
 struct ChecksumTables {
@@ -39,24 +41,36 @@ void launch_xxh32_encode(const uint8_t* src_base, const uint64_t* d_src_off, con
 void launch_xxh32_verify(const BlockDesc* d_desc, uint32_t n_blocks, const uint8_t* dst_base, uint32_t seed,
                          uint32_t mask, int32_t* d_status, cudaStream_t st, uint64_t* launches);
 
-// ---------------- lz4.cu (K3/K4 + LZ4Block framing) ----------------
+// ---------------- lz4_compress.cu (K3: match / parse / emit + write-side LZ4Block framing) ----------------
 extern int g_lz4_hlog, g_lz4d_tile;
-// compress every codec block into scratch (stride block_size); csize[b] = payload bytes (bit 31 = stored RAW);
-// sizes[b] = 21 + payload (input of the packing scan)
-void launch_lz4_compress(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
-                         const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
-                         uint8_t* d_scratch, uint32_t* d_csize, uint64_t* d_sizes, unsigned int* d_counter,
-                         cudaStream_t st, uint64_t* launches);
-// headers + payloads + end marks at their packed offsets (d_scan = exclusive scan of sizes); fills dst_off/dst_len
-void launch_lz4block_pack(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
-                          const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
-                          const uint8_t* d_scratch, const uint32_t* d_csize, const uint32_t* d_hash,
-                          const uint64_t* d_scan, const uint64_t* d_scan_total, uint8_t* dst_base, uint64_t dst_cap,
-                          uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status, cudaStream_t st,
-                          uint64_t* launches);
+// bytes of workspace for one pass over `chunk_blocks` codec blocks (off u16 + ml8 u8 per position, 8-byte records)
+size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size);
+// Codec blocks [b0, b0+m) of the batch, in two halves that may run on different streams (d_ws is handed from one to
+// the other):  launch_lz4_match = phase A (per-position off/ml into d_ws; ev0/ev1 bracket the kernel);
+// launch_lz4_parse_emit = parse -> scan(d_sizes[b0..b0+m), chained on *d_running_total) -> emit (+ 21-byte headers)
+// straight into the blocks' packed positions in dst_base.  d_nseq/d_csize/d_hash/d_sizes are indexed by global block
+// id; afterwards d_sizes[b] holds the packed offset (without the per-stream end marks) and d_csize[b] the payload
+// bytes (bit 31 = stored RAW).
+void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                      const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+                      uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches, cudaEvent_t ev0,
+                      cudaEvent_t ev1);
+void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                           const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
+                           uint32_t block_size, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,
+                           const uint32_t* d_hash, uint64_t* d_sizes, uint64_t* d_running_total, uint64_t* d_scan_ws,
+                           uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches);
+// per stream: dst_off/dst_len, end mark, B2S_E_DST_TOO_SMALL (d_scan = packed block offsets, d_scan_total = their sum)
+void launch_lz4block_stream_meta(const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
+                                 const uint64_t* d_scan, const uint64_t* d_scan_total, uint8_t* dst_base,
+                                 uint64_t dst_cap, uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status,
+                                 cudaStream_t st, uint64_t* launches);
+
+// ---------------- lz4.cu (K4 + read-side LZ4Block framing) ----------------
 // header walk pass 1: per stream block count + decoded bytes; malformed -> status CORRUPT (streams already failed are skipped)
+// d_maxima[0..1] (pre-zeroed) receive the largest originalLen / compressedLen of any codec block of the batch
 void launch_lz4block_count(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
-                           uint64_t* d_nblk, uint64_t* d_olen, int32_t* d_status, cudaStream_t st,
+                           uint64_t* d_nblk, uint64_t* d_olen, uint64_t* d_maxima, int32_t* d_status, cudaStream_t st,
                            uint64_t* launches);
 // header walk pass 2: descriptors at d_blk_base[i]+k; streams that overflow dst_cap get status DST_TOO_SMALL + no-op descriptors
 void launch_lz4block_fill(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
@@ -64,6 +78,14 @@ void launch_lz4block_fill(const uint8_t* src_base, const uint64_t* d_src_off, co
                           int32_t* d_status, BlockDesc* d_desc, cudaStream_t st, uint64_t* launches);
 void launch_lz4_decompress(const BlockDesc* d_desc, uint32_t n_blocks, const uint8_t* src_base, uint8_t* dst_base,
                            int32_t* d_status, unsigned int* d_counter, cudaStream_t st, uint64_t* launches);
+
+// ---------------- lz4_decode.cu (K4: tokens + copy; codec blocks <= 64 KiB) ----------------
+size_t lz4_decode_ws_bytes(uint32_t chunk_blocks, uint32_t max_olen);
+// decodes codec blocks [b0, b0+m): per-sequence records into d_ws, then the byte copies; d_nrec is indexed by global
+// block id.  Malformed blocks set status[stream] = B2S_E_CORRUPT.
+void launch_lz4_decode_chunk(const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t max_olen,
+                             const uint8_t* src_base, uint8_t* dst_base, uint8_t* d_ws, uint32_t* d_nrec,
+                             int32_t* d_status, cudaStream_t st, uint64_t* launches);
 
 // ---------------- gen.cu (bench utility) ----------------
 void launch_gen_terasort(uint8_t* d_dst, uint64_t first_record, uint64_t n_records, uint64_t seed, cudaStream_t st);

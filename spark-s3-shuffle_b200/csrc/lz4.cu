@@ -1,4 +1,5 @@
-// lz4.cu — K3 (LZ4 block compress), K4 (LZ4 block decompress) and the lz4-java LZ4Block stream framing.
+// lz4.cu — K4 (LZ4 block decompress) and the read side of the lz4-java LZ4Block stream framing (K3, the compressor,
+// and the write-side framing live in lz4_compress.cu).
 //
 // Replaces, for spark.io.compression.codec=lz4, what Spark's SerializerManager.wrapStream puts around the streams
 // of shuffle/S3ShuffleMapOutputWriter.scala:140-146 (write) and storage/S3ShuffleReader.scala:107-109 (read):
@@ -22,400 +23,7 @@ namespace b2s {
 
 constexpr int kLz4Threads = 128;
 constexpr int kMinMatch = 4, kMFLimit = 12, kLastLiterals = 5;
-
-__device__ __forceinline__ uint32_t find_stream32(const uint32_t* __restrict__ blk_base, uint32_t n_streams,
-                                                  uint32_t b) {
-  uint32_t lo = 0, hi = n_streams;
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (blk_base[mid] <= b) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K3: compress — one warp per codec block, "window-batched greedy" (specification: orc_lz4_compress_block_win)
-//
-//   per window of 32 positions:
-//     1. every lane hashes its 4 bytes, reads the candidate from the shared-memory table (state before the window;
-//        byte runs use an explicit offset-1 candidate), verifies 4 bytes and measures the match locally up to
-//        8 bytes                                                                          (all lanes in parallel)
-//     2. the warp walks the window greedily with uniform bit operations on the ballot mask: lowest matching
-//        position >= cursor, its length by shuffle (cooperative extension only when the local 8 bytes were all
-//        equal) — about a dozen instructions per selected sequence
-//     3. literal counts, encoded sizes and output offsets of all selected sequences by one warp suffix-sum
-//     4. each selected lane emits its own sequence (token, <= 16 literals, offset, <= 2 length bytes); rare longer
-//        literal runs / lengths go through a cooperative slow path
-//     5. all 32 positions are inserted; a slot hit twice is settled by a read-back so the highest position wins
-//   Measured motivation (profiles/): terasort-shaped data has ~4400 sequences per 32 KiB block (7.5 B each), so the
-//   per-sequence instruction count is what bounds this kernel, not HBM.
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_store_len_ext(uint8_t* o, int nb, int r, int lane) {
-  for (int j = lane; j < nb; j += 32) o[j] = (j == nb - 1) ? (uint8_t)(r - 255 * (nb - 1)) : (uint8_t)255;
-}
-__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int n,
-                                                int lane) {
-  if (n >= 96) {
-    group_copy<32>(dst, src, (uint32_t)n, lane);
-  } else {
-    for (int j = lane; j < n; j += 32) dst[j] = __ldg(src + j);
-  }
-}
-// cooperative emit of one sequence (mlen == 0: final literal run without a match part)
-__device__ __forceinline__ void warp_emit_seq(uint8_t* __restrict__ o, const uint8_t* __restrict__ lit_src, int lit,
-                                              int off, int mlen, int lane) {
-  const int ml = mlen - kMinMatch;
-  const int nbL = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
-  if (lane == 0) o[0] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mlen ? (ml < 15 ? ml : 15) : 0));
-  if (nbL) warp_store_len_ext(o + 1, nbL, lit - 15, lane);
-  warp_copy_bytes(o + 1 + nbL, lit_src, lit, lane);
-  if (mlen) {
-    uint8_t* q = o + 1 + nbL + lit;
-    if (lane == 0) q[0] = (uint8_t)off;
-    if (lane == 1) q[1] = (uint8_t)(off >> 8);
-    if (ml >= 15) warp_store_len_ext(q + 2, (ml - 15) / 255 + 1, ml - 15, lane);
-  }
-}
-template <int HLOG>
-__global__ void __launch_bounds__(kLz4Threads, (HLOG >= 13 ? 3 : HLOG == 12 ? 6 : 8)) lz4_compress_kernel(
-    const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
-    const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
-    uint8_t* __restrict__ scratch, uint32_t* __restrict__ csize, uint64_t* __restrict__ sizes,
-    unsigned int* __restrict__ work_counter) {
-  extern __shared__ __align__(16) uint16_t smem_tables[];
-  constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  uint16_t* table = smem_tables + (size_t)(threadIdx.x >> 5) * (1 << HLOG);
-
-  for (;;) {
-    uint32_t b = 0;
-    if (lane == 0) b = atomicAdd(work_counter, 1u);
-    b = __shfl_sync(FULL, b, 0);
-    if (b >= n_blocks) break;
-
-    const uint32_t si = find_stream32(blk_base, n_streams, b);
-    const uint64_t boff = (uint64_t)(b - blk_base[si]) * block_size;
-    const uint64_t rem = src_len[si] - boff;
-    const int n = (int)(rem < block_size ? rem : block_size);
-    const uint8_t* __restrict__ s = src_base + src_off[si] + boff;
-    uint8_t* __restrict__ out = scratch + (uint64_t)b * block_size;
-    const int cap = n - 1;  // LZ4BlockOutputStream stores RAW when compressedLength >= originalLength
-
-    {
-      uint4* t4 = reinterpret_cast<uint4*>(table);
-      for (int j = lane; j < (1 << HLOG) / 8; j += 32) t4[j] = make_uint4(0, 0, 0, 0);
-    }
-    __syncwarp();
-
-    int op = 0, anchor = 0, pos = 0;
-    bool fail = false;
-    if (n >= kMFLimit + 1) {
-      const int mflimit = n - kMFLimit;
-      const int matchlimit = n - kLastLiterals;
-      while (pos <= mflimit) {
-        // ---- 1. lookup + local match length (<= 8) for all 32 positions.  Lane l owns window position r = 31 - l:
-        //         the hardware resolves same-address shared stores in favour of the lowest lane, so with this
-        //         mapping a contested hash slot receives the highest position on the first store (step 4).
-        const int r_me = 31 - lane;
-        const int p = pos + r_me;
-        const bool valid = p <= mflimit;
-        uint32_t v = 0, v2 = 0, h = 0;
-        int cand = 0, ml = 0;
-        bool ok = false;
-        if (valid) {
-          const uintptr_t a = reinterpret_cast<uintptr_t>(s + p);
-          const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-          const unsigned sh = (a & 3u) * 8u;
-          const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = sh ? __ldg(w + 2) : 0u;
-          v = __funnelshift_r(w0, w1, sh);
-          v2 = __funnelshift_r(w1, w2, sh);
-          h = (v * 2654435761u) >> (32 - HLOG);
-          cand = table[h];
-          const uint32_t prev = p > 0 ? (uint32_t)__ldg(s + p - 1) : (~v & 0xffu);
-          uint32_t x = 1;
-          if (v == prev * 0x01010101u) {  // byte run: offset-1 candidate (what a sequential hash table would hold)
-            ok = true;
-            cand = p - 1;
-            x = __funnelshift_r(v, v2, 24) ^ v2;  // bytes p+3..p+6 against p+4..p+7
-          } else if (cand < p) {
-            const uintptr_t ca = reinterpret_cast<uintptr_t>(s + cand);
-            const uint32_t* cw = reinterpret_cast<const uint32_t*>(ca & ~uintptr_t(3));
-            const unsigned csh = (ca & 3u) * 8u;
-            const uint32_t c0 = __ldg(cw), c1 = __ldg(cw + 1);
-            if (__funnelshift_r(c0, c1, csh) == v) {
-              ok = true;
-              const uint32_t c2 = csh ? __ldg(cw + 2) : 0u;
-              x = __funnelshift_r(c1, c2, csh) ^ v2;
-            }
-          }
-          if (ok) {
-            ml = x ? 4 + ((__ffs(x) - 1) >> 3) : 8;
-            const int lim = matchlimit - p;
-            if (ml > lim) ml = lim;
-          }
-        }
-        const unsigned posmask = __brev(__ballot_sync(FULL, ok));  // bit r <-> window position r
-
-        // ---- 2. greedy walk over the window: uniform bit operations, ~a dozen instructions per selected sequence
-        int cur = 0;          // window-relative parse cursor
-        unsigned selmask = 0; // positions whose match the parse takes
-        for (;;) {
-          const unsigned t = posmask & (FULL << cur);
-          if (!t) break;
-          const int r = __ffs(t) - 1;
-          int mlr = __shfl_sync(FULL, ml, 31 - r);
-          if (mlr == 8) {  // local 8 bytes all equal: extend cooperatively, 32 bytes per ballot
-            const int m = pos + r;
-            const int maxl = matchlimit - m;
-            if (maxl > 8) {
-              const int c = __shfl_sync(FULL, cand, 31 - r);
-              int k = 8 + lane;
-              for (;;) {
-                const bool ne = (k >= maxl) || (__ldg(s + m + k) != __ldg(s + c + k));
-                const unsigned nb = __ballot_sync(FULL, ne);
-                if (nb) {
-                  mlr = k - lane + __ffs(nb) - 1;
-                  break;
-                }
-                k += 32;
-              }
-              if (r == r_me) ml = mlr;
-            }
-          }
-          selmask |= 1u << r;
-          cur = r + mlr;
-          if (cur >= 32) break;
-        }
-
-        // ---- 3. sizes and output offsets for all selected sequences at once (suffix sum over lanes = prefix over positions)
-        const bool sel = (selmask >> r_me) & 1u;
-        const unsigned below = selmask & ((1u << r_me) - 1u);  // selected positions before mine
-        const int rp = 31 - __clz(below);                      // -1 when none
-        const int ml_prev = __shfl_sync(FULL, ml, below ? 31 - rp : lane);
-        const int lit = p - (below ? pos + rp + ml_prev : anchor);
-        const int mlc = ml - kMinMatch;
-        int sz = 0;
-        if (sel) {
-          sz = 3 + lit;
-          if (lit >= 15) sz += (lit - 15) / 255 + 1;
-          if (mlc >= 15) sz += (mlc - 15) / 255 + 1;
-        }
-        int suf = sz;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_down_sync(FULL, suf, d);
-          if (lane + d < 32) suf += t;
-        }
-        const int total = __shfl_sync(FULL, suf, 0);
-        if (op + total > cap) {
-          fail = true;
-          break;
-        }
-        const int my_op = op + suf - sz;  // sequences at earlier positions (higher lanes) come first
-
-        // ---- 4. emit: every selected lane writes its own sequence; only very long literal runs / lengths go cooperative
-        bool slow = false;
-        if (sel) {
-          if (lit <= 16 && mlc < 15 + 510) {
-            uint8_t* q = out + my_op;
-            *q++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mlc < 15 ? mlc : 15));
-            if (lit >= 15) *q++ = (uint8_t)(lit - 15);
-            const uint8_t* ls = s + p - lit;
-            for (int j = 0; j < lit; j++) q[j] = __ldg(ls + j);
-            q += lit;
-            const int off = p - cand;
-            q[0] = (uint8_t)off;
-            q[1] = (uint8_t)(off >> 8);
-            if (mlc >= 15) {
-              int rem = mlc - 15;
-              q += 2;
-              if (rem >= 255) {
-                *q++ = 255;
-                rem -= 255;
-              }
-              *q = (uint8_t)rem;
-            }
-          } else {
-            slow = true;
-          }
-        }
-        unsigned slowmask = __ballot_sync(FULL, slow);
-        while (slowmask) {
-          const int l = __ffs(slowmask) - 1;
-          slowmask &= slowmask - 1;
-          const int lit_r = __shfl_sync(FULL, lit, l);
-          const int ml_r = __shfl_sync(FULL, ml, l);
-          const int op_r = __shfl_sync(FULL, my_op, l);
-          const int cand_r = __shfl_sync(FULL, cand, l);
-          const int m = pos + 31 - l;
-          warp_emit_seq(out + op_r, s + m - lit_r, lit_r, m - cand_r, ml_r, lane);
-        }
-        op += total;
-        if (selmask) anchor = pos + cur;
-
-        // ---- 5. insert the window; a read-back settles slots hit twice so that the highest position wins
-        __syncwarp();
-        if (valid) table[h] = (uint16_t)p;
-        __syncwarp();
-        for (;;) {
-          const bool lost = valid && table[h] < (uint16_t)p;
-          if (!__ballot_sync(FULL, lost)) break;
-          if (lost) table[h] = (uint16_t)p;
-          __syncwarp();
-        }
-        pos += cur > 32 ? cur : 32;
-      }
-    }
-    if (!fail) {
-      const int lit = n - anchor;
-      const int need = 1 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);
-      if (op + need > cap) {
-        fail = true;
-      } else {
-        warp_emit_seq(out + op, s + anchor, lit, 0, 0, lane);
-        op += need;
-      }
-    }
-    if (lane == 0) {
-      csize[b] = fail ? ((uint32_t)n | 0x80000000u) : (uint32_t)op;
-      sizes[b] = 21u + (uint64_t)(fail ? n : op);
-    }
-    __syncwarp();
-  }
-}
-
-template <int HLOG>
-static void launch_lz4_compress_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
-                                  const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks,
-                                  uint32_t block_size, uint8_t* d_scratch, uint32_t* d_csize, uint64_t* d_sizes,
-                                  unsigned int* d_counter, cudaStream_t st) {
-  constexpr int kWarps = kLz4Threads / 32;
-  const size_t smem = (size_t)kWarps * (2u << HLOG);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(lz4_compress_kernel<HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_compress_kernel<HLOG>, kLz4Threads, smem);
-  if (per_sm < 1) per_sm = 1;
-  uint64_t want = ((uint64_t)n_blocks + kWarps - 1) / kWarps;
-  uint64_t grid = (uint64_t)kSMs * per_sm;
-  if (grid > want) grid = want;
-  lz4_compress_kernel<HLOG><<<(unsigned)grid, kLz4Threads, smem, st>>>(src_base, d_src_off, d_src_len, d_blk_base,
-                                                                      n_streams, n_blocks, block_size, d_scratch,
-                                                                      d_csize, d_sizes, d_counter);
-}
-
-int g_lz4_hlog = 12;   // tuning knobs (api.cu reads B2S_LZ4_HLOG / B2S_LZ4D_TILE once at init); 12 is the specified default
-int g_lz4d_tile = 8;
-
-void launch_lz4_compress(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
-                         const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
-                         uint8_t* d_scratch, uint32_t* d_csize, uint64_t* d_sizes, unsigned int* d_counter,
-                         cudaStream_t st, uint64_t* launches) {
-  if (!n_blocks) return;
-  cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), st);
-#define B2S_LZ4C(H)                                                                                                  \
-  launch_lz4_compress_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, n_blocks, block_size, d_scratch,  \
-                           d_csize, d_sizes, d_counter, st)
-  switch (g_lz4_hlog) {
-    case 10: B2S_LZ4C(10); break;
-    case 11: B2S_LZ4C(11); break;
-    case 13: B2S_LZ4C(13); break;
-    default: B2S_LZ4C(12); break;
-  }
-#undef B2S_LZ4C
-  *launches += 1;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// LZ4Block framing, write side
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int lz4b_level(uint32_t block_size) {
-  int bits = 32 - __clz(block_size - 1);
-  int lvl = bits - 10;
-  return lvl < 0 ? 0 : lvl;
-}
-
-__device__ __forceinline__ uint8_t lz4b_header_byte(int j, int token, uint32_t clen, uint32_t olen, uint32_t check) {
-  // "LZ4Block" = 4C 5A 34 42 6C 6F 63 6B
-  const uint64_t magic = 0x6B636F6C42345A4Cull;
-  if (j < 8) return (uint8_t)(magic >> (8 * j));
-  if (j == 8) return (uint8_t)token;
-  if (j < 13) return (uint8_t)(clen >> (8 * (j - 9)));
-  if (j < 17) return (uint8_t)(olen >> (8 * (j - 13)));
-  return (uint8_t)(check >> (8 * (j - 17)));
-}
-
-// per stream: packed offset/length, end mark, capacity check
-__global__ void lz4block_stream_meta_kernel(const uint32_t* __restrict__ blk_base, uint32_t n_streams,
-                                            uint32_t n_blocks, uint32_t block_size, const uint64_t* __restrict__ scan,
-                                            const uint64_t* __restrict__ scan_total, uint8_t* __restrict__ dst_base,
-                                            uint64_t dst_cap, uint64_t* __restrict__ dst_off,
-                                            uint64_t* __restrict__ dst_len, int32_t* __restrict__ status) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_streams) return;
-  const uint32_t b0 = blk_base[i], b1 = blk_base[i + 1];
-  const uint64_t s0 = b0 < n_blocks ? scan[b0] : *scan_total;
-  const uint64_t s1 = b1 < n_blocks ? scan[b1] : *scan_total;
-  const uint64_t off = s0 + 21ull * i;
-  const uint64_t len = (s1 - s0) + 21ull;
-  dst_off[i] = off;
-  dst_len[i] = len;
-  if (off + len > dst_cap) {
-    status[i] = B2S_E_DST_TOO_SMALL;
-    return;
-  }
-  uint8_t* e = dst_base + off + len - 21;
-  const int token = 0x10 | lz4b_level(block_size);
-#pragma unroll
-  for (int j = 0; j < 21; j++) e[j] = lz4b_header_byte(j, token, 0, 0, 0);
-}
-
-// one warp per codec block: header + payload to the packed position
-__global__ void __launch_bounds__(256) lz4block_pack_kernel(
-    const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
-    const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
-    const uint8_t* __restrict__ scratch, const uint32_t* __restrict__ csize, const uint32_t* __restrict__ hash,
-    const uint64_t* __restrict__ scan, uint8_t* __restrict__ dst_base, uint64_t dst_cap,
-    const int32_t* __restrict__ status) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= n_blocks) return;
-  const uint32_t si = find_stream32(blk_base, n_streams, b);
-  if (status[si] != 0) return;
-  const uint64_t boff = (uint64_t)(b - blk_base[si]) * block_size;
-  const uint64_t rem = src_len[si] - boff;
-  const uint32_t olen = (uint32_t)(rem < block_size ? rem : block_size);
-  const uint32_t cs = csize[b];
-  const bool raw = cs & 0x80000000u;
-  const uint32_t clen = cs & 0x7fffffffu;
-  uint8_t* o = dst_base + scan[b] + 21ull * si;
-  const int token = (raw ? 0x10 : 0x20) | lz4b_level(block_size);
-  if (lane < 21) o[lane] = lz4b_header_byte(lane, token, clen, olen, hash[b] & 0x0FFFFFFFu);
-  const uint8_t* payload = raw ? src_base + src_off[si] + boff : scratch + (uint64_t)b * block_size;
-  group_copy<32>(o + 21, payload, clen, lane);
-}
-
-void launch_lz4block_pack(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
-                          const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
-                          const uint8_t* d_scratch, const uint32_t* d_csize, const uint32_t* d_hash,
-                          const uint64_t* d_scan, const uint64_t* d_scan_total, uint8_t* dst_base, uint64_t dst_cap,
-                          uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status, cudaStream_t st,
-                          uint64_t* launches) {
-  if (!n_streams) return;
-  lz4block_stream_meta_kernel<<<(n_streams + 255) / 256, 256, 0, st>>>(d_blk_base, n_streams, n_blocks, block_size,
-                                                                       d_scan, d_scan_total, dst_base, dst_cap,
-                                                                       d_dst_off, d_dst_len, d_status);
-  *launches += 1;
-  if (n_blocks) {
-    lz4block_pack_kernel<<<(n_blocks + 7) / 8, 256, 0, st>>>(src_base, d_src_off, d_src_len, d_blk_base, n_streams,
-                                                            n_blocks, block_size, d_scratch, d_csize, d_hash, d_scan,
-                                                            dst_base, dst_cap, d_status);
-    *launches += 1;
-  }
-}
+int g_lz4d_tile = 8;  // B2S_LZ4D_TILE (api.cu reads it once at init)
 
 // ------------------------------------------------------------------------------------------------------------
 // LZ4Block framing, read side: header walk (LZ4BlockInputStream.refill [U])
@@ -451,7 +59,8 @@ __device__ __forceinline__ bool lz4b_header_valid(const Lz4bHeader& h) {
 template <bool FILL>
 __global__ void lz4block_walk_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
                                      const uint64_t* __restrict__ src_len, uint32_t n, uint64_t* __restrict__ nblk,
-                                     uint64_t* __restrict__ olen_total, const uint64_t* __restrict__ blk_base,
+                                     uint64_t* __restrict__ olen_total, unsigned long long* __restrict__ maxima,
+                                     const uint64_t* __restrict__ blk_base,
                                      const uint64_t* __restrict__ dst_off, uint64_t dst_cap,
                                      int32_t* __restrict__ status, BlockDesc* __restrict__ desc) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -465,6 +74,7 @@ __global__ void lz4block_walk_kernel(const uint8_t* __restrict__ src_base, const
   const uint8_t* p = src_base + src_off[i];
   const uint64_t len = src_len[i];
   uint64_t ip = 0, cnt = 0, total = 0;
+  uint32_t max_olen = 0, max_clen = 0;
   bool bad = false;
   bool too_small = false;
   if (FILL) too_small = (dst_off[i] + olen_total[i] > dst_cap);
@@ -501,6 +111,10 @@ __global__ void lz4block_walk_kernel(const uint8_t* __restrict__ src_base, const
       desc[blk_base[i] + cnt] = d;
     }
     cnt++;
+    if (!FILL) {
+      max_olen = max_olen > (uint32_t)h.olen ? max_olen : (uint32_t)h.olen;
+      max_clen = max_clen > (uint32_t)h.clen ? max_clen : (uint32_t)h.clen;
+    }
     total += (uint64_t)h.olen;
     ip += (uint64_t)h.clen;
   }
@@ -512,17 +126,22 @@ __global__ void lz4block_walk_kernel(const uint8_t* __restrict__ src_base, const
     }
     nblk[i] = cnt;
     olen_total[i] = total;
+    if (cnt) {  // largest codec block of the batch (selects the decode path and sizes its records)
+      atomicMax(maxima, (unsigned long long)max_olen);
+      atomicMax(maxima + 1, (unsigned long long)max_clen);
+    }
   } else if (too_small) {
     status[i] = B2S_E_DST_TOO_SMALL;
   }
 }
 
 void launch_lz4block_count(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
-                           uint64_t* d_nblk, uint64_t* d_olen, int32_t* d_status, cudaStream_t st,
+                           uint64_t* d_nblk, uint64_t* d_olen, uint64_t* d_maxima, int32_t* d_status, cudaStream_t st,
                            uint64_t* launches) {
   if (!n) return;
   lz4block_walk_kernel<false><<<(n + 127) / 128, 128, 0, st>>>(src_base, d_src_off, d_src_len, n, d_nblk, d_olen,
-                                                              nullptr, nullptr, 0, d_status, nullptr);
+                                                              (unsigned long long*)d_maxima, nullptr, nullptr, 0,
+                                                              d_status, nullptr);
   *launches += 1;
 }
 
@@ -531,7 +150,8 @@ void launch_lz4block_fill(const uint8_t* src_base, const uint64_t* d_src_off, co
                           int32_t* d_status, BlockDesc* d_desc, cudaStream_t st, uint64_t* launches) {
   if (!n) return;
   lz4block_walk_kernel<true><<<(n + 127) / 128, 128, 0, st>>>(src_base, d_src_off, d_src_len, n, nullptr, d_olen,
-                                                             d_blk_base, d_dst_off, dst_cap, d_status, d_desc);
+                                                             nullptr, d_blk_base, d_dst_off, dst_cap, d_status,
+                                                             d_desc);
   *launches += 1;
 }
 

@@ -1,0 +1,574 @@
+// lz4_compress.cu — K3: LZ4 block compression as three kernels (specification: orc_lz4_compress_block_win in oracle/).
+//
+// Replaces liblz4's LZ4_compress_default as driven by lz4-java's LZ4BlockOutputStream [U] under
+// SerializerManager.wrapStream on the streams of shuffle/S3ShuffleMapOutputWriter.scala:140-146.
+//
+// Why three kernels: an LZ77 coder has one inherently serial piece — the greedy parse — and two pieces that are not.
+// Measured on the first, single-kernel version (profiles/r1a): 10.4 warp-instructions per input byte because the
+// serial parse ran on a whole warp (4 of 32 lanes useful).  HBM, on the other hand, sat at 1.2 % of peak.  So the
+// serial piece is isolated and given one THREAD per codec block, and the abundant HBM bandwidth carries small
+// intermediates between the phases:
+//
+//   A  lz4_match_kernel   warp per block, all lanes busy, no parse dependency: for every position p of a FIXED window
+//                         of 32 positions look the 4 bytes up in a per-warp u16 hash table in shared memory (state
+//                         before the window; byte runs use the offset-1 candidate), verify the candidate, measure
+//                         the match locally up to 8 bytes  ->  off[p] (u16, 0 = none), ml8[p] (u8);
+//                         then insert the 32 positions (highest position wins a slot, deterministic).
+//   B  lz4_parse_kernel   THREAD per block: greedy walk over ml8[] (8 positions per 64-bit load), long matches
+//                         extended on the source; emits one 8-byte record per sequence with its output offset
+//                         (running sum — no scan needed later), decides RAW (compressedLength >= originalLength).
+//   C  lz4_emit_kernel    warp per block, LANE per sequence (dense): token, literals, offset, length bytes written
+//                         straight to the block's final position in the packed destination (after an exclusive scan
+//                         of the block sizes), together with the 21-byte LZ4Block header.  No scratch copy.
+//
+// Intermediates per input byte: off 2 B + ml8 1 B + records <= 2 B; the runtime processes at most kChunk blocks per
+// pass so the workspace stays bounded.  Algorithmic bytes stay (1 + r) per input byte; the extra traffic is reported
+// by ncu's dram__bytes (profiles/).
+#include "kernels.h"
+
+namespace b2s {
+
+constexpr int kMinMatch = 4, kMFLimit = 12, kLastLiterals = 5;
+constexpr int kMatchWarps = 9;  // 9 warps x 8 KiB tables = 72 KiB per CTA, 3 CTAs per SM = 27 warps
+
+__device__ __forceinline__ uint32_t find_stream_of_block(const uint32_t* __restrict__ blk_base, uint32_t n_streams,
+                                                         uint32_t b) {
+  uint32_t lo = 0, hi = n_streams;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (blk_base[mid] <= b) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+struct BlockSpan {
+  const uint8_t* s;
+  int n;
+  uint32_t stream;
+};
+__device__ __forceinline__ BlockSpan block_span(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
+                                                const uint64_t* __restrict__ src_len,
+                                                const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b,
+                                                uint32_t block_size) {
+  BlockSpan r;
+  r.stream = find_stream_of_block(blk_base, n_streams, b);
+  const uint64_t boff = (uint64_t)(b - blk_base[r.stream]) * block_size;
+  const uint64_t rem = src_len[r.stream] - boff;
+  r.n = (int)(rem < block_size ? rem : block_size);
+  r.s = src_base + src_off[r.stream] + boff;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// A: match finding
+// ------------------------------------------------------------------------------------------------------------
+// Candidate words of one window, requested in iteration k and consumed in iteration k+1 so that their latency is
+// covered by a whole iteration of table work (the hash-table chain window -> insert -> next lookup never waits on
+// a global load).
+struct PendingWindow {
+  uint32_t c0, c1, c2, v, v2;
+  int p, cand, pos;
+  unsigned csh;
+  bool live;  // lane holds a position <= mflimit whose candidate is older than the position
+};
+
+template <int HLOG>
+__global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match_kernel(
+    const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
+    const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+    uint32_t stride, uint16_t* __restrict__ offarr, uint16_t* __restrict__ mlarr,
+    unsigned int* __restrict__ work_counter) {
+  extern __shared__ __align__(16) uint16_t smem_tables[];
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  uint16_t* table = smem_tables + (size_t)(threadIdx.x >> 5) * (1 << HLOG);
+  // Lane l owns window position r = 31 - l: same-address shared stores resolve in favour of the lowest lane on this
+  // part, so a contested hash slot receives the highest position on the first store and the read-back that
+  // guarantees determinism almost never iterates.
+  const int r_me = 31 - lane;
+
+  for (;;) {
+    uint32_t bl = 0;
+    if (lane == 0) bl = atomicAdd(work_counter, 1u);
+    bl = __shfl_sync(FULL, bl, 0);
+    if (bl >= m) break;
+    const BlockSpan B = block_span(src_base, src_off, src_len, blk_base, n_streams, b0 + bl, block_size);
+    const uint8_t* __restrict__ s = B.s;
+    const int n = B.n;
+    uint16_t* oq = offarr + (size_t)bl * stride + r_me;
+    uint16_t* mq = mlarr + (size_t)bl * stride + r_me;
+    {
+      uint4* t4 = reinterpret_cast<uint4*>(table);
+      for (int j = lane; j < (1 << HLOG) / 8; j += 32) t4[j] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    if (n < kMFLimit + 1) continue;
+    const int mflimit = n - kMFLimit;
+    const int matchlimit = n - kLastLiterals;
+
+    // carry of the previous window's last position (window position 31 = lane 0): its offset and full length
+    uint32_t carry_off = 0;
+    int carry_L = 0;
+
+    // Finishes a window whose candidate words have arrived: verify, local match length (<= 8), FULL match length,
+    // stores.  Full lengths come without touching the source almost always: if positions p and p+1 both matched with
+    // the same offset, then L[p] = L[p+1] + 1 (same alignment of the comparison).  So inside a window every segment
+    // of equal offsets takes its lengths from the segment's last position q: L[p] = L[q] + (q - p), and L[q] is the
+    // local length unless q is itself "long" (8 local bytes equal, room to grow) — only those segment ends are
+    // measured on the source, cooperatively, 32 bytes per ballot round.  A run that fills the whole window and
+    // continues the previous window's run takes the length of its last position from the carry instead.
+    auto finish = [&](const PendingWindow& W) {
+      const bool ok = W.live && __funnelshift_r(W.c0, W.c1, W.csh) == W.v;
+      const uint32_t x = __funnelshift_r(W.c1, W.c2, W.csh) ^ W.v2;
+      int ml = x ? 4 + ((__ffs(x) - 1) >> 3) : 8;
+      const int lim = matchlimit - W.p;
+      ml = ml < lim ? ml : lim;
+      const bool lng = ok && x == 0 && lim > 8;
+      const uint32_t off = ok ? (uint32_t)(W.p - W.cand) : 0u;
+      int L = ok ? ml : 0;
+      const unsigned lngmask = __brev(__ballot_sync(FULL, lng));  // bit r <-> window position r
+      if (lngmask) {
+        const uint32_t next_off = __shfl_up_sync(FULL, off, 1);   // position r+1 lives in lane-1
+        const bool brk = lane == 0 || off == 0 || off != next_off;
+        const unsigned brkmask = __brev(__ballot_sync(FULL, brk));  // segment ends; bit 31 always set
+        unsigned extmask = brkmask & lngmask;
+        const uint32_t off0 = __shfl_sync(FULL, off, 31);  // position 0
+        if ((extmask >> 31) && (brkmask & 0x7fffffffu) == 0 && off0 == carry_off) {
+          extmask &= 0x7fffffffu;  // one run through the whole window, continuing the carried one
+          if (lane == 0) L = carry_L - 32;
+        }
+        while (extmask) {
+          const int q = __ffs(extmask) - 1;
+          extmask &= extmask - 1;
+          const int oq_ = (int)__shfl_sync(FULL, off, 31 - q);
+          const int mpos = W.pos + q;
+          const int maxl = matchlimit - mpos;
+          const uint8_t* a = s + mpos + lane;
+          const uint8_t* c = a - oq_;
+          int Lq = maxl;
+          for (int base = 8;; base += 32) {
+            const int k = base + lane;
+            const bool stop = k >= maxl || __ldg(a + base) != __ldg(c + base);
+            const unsigned bm = __ballot_sync(FULL, stop);
+            if (bm) {
+              const int e = base + __ffs(bm) - 1;
+              Lq = e < maxl ? e : maxl;
+              break;
+            }
+          }
+          if (r_me == q) L = Lq;
+        }
+        // lengths inside segments from their ends
+        const int d = __ffs(brkmask >> r_me) - 1;  // distance to my segment's last position
+        const int Lend = __shfl_sync(FULL, L, lane - d);
+        if (off) L = Lend + d;
+      }
+      carry_off = __shfl_sync(FULL, off, 0);
+      carry_L = __shfl_sync(FULL, L, 0);
+      __stcs(oq, (uint16_t)off);  // position < stride always (stride = block_size rounded up to 32)
+      __stcs(mq, (uint16_t)L);
+      oq += 32;
+      mq += 32;
+    };
+
+    // per-lane word pointer for the prefetched source words of full windows; (s + pos + r) & 3 is window-invariant
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(s + (r_me <= mflimit ? r_me : mflimit));
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0 & ~uintptr_t(3));
+    const unsigned sh = (reinterpret_cast<uintptr_t>(s + r_me) & 3u) * 8u;
+    uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+    uint32_t carry_v = 0;
+    // one window: hash + lookup, request the candidate words into N, finish the previous window F, insert
+    auto step = [&](int pos, PendingWindow& N, const PendingWindow& F, bool have_prev) {
+      const bool full = pos + 31 <= mflimit;  // uniform
+      const int p = pos + r_me;
+      const bool valid = p <= mflimit;
+      const int pc = valid ? p : mflimit;
+      uint32_t v, v2;
+      if (full) {
+        v = __funnelshift_r(w0, w1, sh);
+        v2 = __funnelshift_r(w1, w2, sh);
+        if (pos + 63 <= mflimit) {  // the next window is full as well: request its words now
+          wp += 8;
+          w0 = __ldg(wp);
+          w1 = __ldg(wp + 1);
+          w2 = __ldg(wp + 2);
+        }
+      } else {  // last, partial window: clamped positions, plain loads
+        v = ld32u_ro(s + pc);
+        v2 = ld32u_ro(s + pc + 4);
+      }
+      // byte run: the 4 bytes at p-1 equal those at p, i.e. v(p-1) == v(p) — the neighbour lane's value
+      const uint32_t vprev = __shfl_down_sync(FULL, v, 1);
+      bool rle = vprev == v;
+      if (lane == 31) rle = pos > 0 && carry_v == v;
+      carry_v = __shfl_sync(FULL, v, 0);
+      const uint32_t h = (v * 2654435761u) >> (32 - HLOG);
+      int cand = table[h];
+      if (rle) cand = pc - 1;
+      const bool older = cand < pc;
+      if (!older) cand = 0;  // keep the loads in bounds; the result is discarded
+      {
+        const uintptr_t ca = reinterpret_cast<uintptr_t>(s + cand);
+        const uint32_t* cw = reinterpret_cast<const uint32_t*>(ca & ~uintptr_t(3));
+        N.csh = (ca & 3u) * 8u;
+        N.c0 = __ldg(cw);
+        N.c1 = __ldg(cw + 1);
+        N.c2 = __ldg(cw + 2);  // cand + 11 < p + 11 <= n - 1
+      }
+      N.v = v;
+      N.v2 = v2;
+      N.p = pc;
+      N.cand = cand;
+      N.pos = pos;
+      N.live = valid && older;
+
+      if (have_prev) finish(F);  // window k-1: its candidate words were requested one iteration ago
+
+      // insert window k; a read-back settles slots hit twice so that the highest position wins
+      __syncwarp();
+      if (valid) table[h] = (uint16_t)p;
+      __syncwarp();
+      for (;;) {
+        const bool lost = valid && table[h] < (uint16_t)p;
+        if (!__ballot_sync(FULL, lost)) break;
+        if (lost) table[h] = (uint16_t)p;
+        __syncwarp();
+      }
+    };
+
+    // two windows per trip, the pending-window registers ping-pong (no copies)
+    PendingWindow PA, PB;
+    PA.live = PB.live = false;
+    PA.c0 = PA.c1 = PA.c2 = PA.v = PA.v2 = PA.csh = 0;
+    PA.p = PA.cand = PA.pos = 0;
+    PB = PA;
+    bool last_is_a = true;
+    for (int pos = 0; pos <= mflimit; pos += 64) {
+      step(pos, PA, PB, pos > 0);
+      last_is_a = true;
+      if (pos + 32 > mflimit) break;
+      step(pos + 32, PB, PA, true);
+      last_is_a = false;
+    }
+    if (last_is_a) finish(PA); else finish(PB);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// B: greedy parse, one thread per codec block
+// ------------------------------------------------------------------------------------------------------------
+// record: x = literal start | literal count << 16 ; y = match length (0 = final literal run) | output offset << 16
+//
+// The walk is a fixed-trip loop over groups of 4 positions (one 64-bit load of ml[], next group prefetched).  A match
+// is at least 4 long, so at most one sequence starts per group: every iteration is the same straight-line code for
+// all 32 lanes (= 32 blocks), no source access, no data-dependent trip counts.
+__global__ void __launch_bounds__(64) lz4_parse_kernel(
+    const uint64_t* __restrict__ src_len, const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0,
+    uint32_t m, uint32_t block_size, uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ mlarr,
+    uint2* __restrict__ seqarr, uint32_t* __restrict__ nseq, uint32_t* __restrict__ csize,
+    uint64_t* __restrict__ sizes) {
+  const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= m) return;
+  const uint32_t b = b0 + bl;
+  const uint32_t si = find_stream_of_block(blk_base, n_streams, b);
+  const uint64_t rem = src_len[si] - (uint64_t)(b - blk_base[si]) * block_size;
+  const int n = (int)(rem < block_size ? rem : block_size);
+  const int cap = n - 1;  // LZ4BlockOutputStream stores RAW when compressedLength >= originalLength
+  const unsigned long long* __restrict__ mlw =
+      reinterpret_cast<const unsigned long long*>(mlarr + (size_t)bl * stride);
+  uint2* __restrict__ seq = seqarr + (size_t)bl * max_seq;
+  int p = 0, anchor = 0, op = 0;
+  uint32_t ns = 0;
+  bool fail = false;
+  const int mflimit = n - kMFLimit;
+  if (mflimit >= 0) {
+    const int groups = (mflimit >> 2) + 1;
+    unsigned long long nxt = __ldcs(mlw);
+    for (int g = 0; g < groups; g++) {
+      const unsigned long long cur = nxt;
+      nxt = __ldcs(mlw + (g + 1 < groups ? g + 1 : g));
+      // each lane streams through its own block, so a miss costs a full DRAM round trip (~2000 cycles) against
+      // ~150 cycles of work per group: pull the sector needed 8 sectors (32 groups) from now into L1 already
+      if ((g & 3) == 0 && g + 32 < groups) asm volatile("prefetch.global.L1 [%0];" ::"l"(mlw + g + 32));
+      const int rel = p - 4 * g;  // >= 0; >= 4 while a match taken earlier still covers this group
+      if (rel < 4) {
+        const unsigned long long w = cur >> (16 * rel);
+        if (w) {
+          const int bit = (__ffsll((long long)w) - 1) & ~15;
+          p += bit >> 4;
+          const int ml = (int)((w >> bit) & 0xffffu);
+          const int lit = p - anchor;
+          const int mlc = ml - kMinMatch;
+          int size = 3 + lit;
+          if (lit >= 15) size += (lit - 15) / 255 + 1;
+          if (mlc >= 15) size += (mlc - 15) / 255 + 1;
+          if (op + size > cap) {
+            fail = true;
+            break;
+          }
+          seq[ns++] = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)ml | ((uint32_t)op << 16));
+          op += size;
+          p += ml;
+          anchor = p;
+        } else {
+          p = 4 * g + 4;
+        }
+      }
+    }
+  }
+  if (!fail) {
+    const int lit = n - anchor;
+    const int need = 1 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);
+    if (op + need > cap) {
+      fail = true;
+    } else {
+      seq[ns++] = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)op << 16);
+      op += need;
+    }
+  }
+  nseq[b] = ns;
+  csize[b] = fail ? ((uint32_t)n | 0x80000000u) : (uint32_t)op;
+  sizes[b] = 21u + (uint64_t)(fail ? n : op);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// C: emission, one lane per sequence, into the block's final packed position; also writes the LZ4Block header
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lz4b_level(uint32_t block_size) {
+  int bits = 32 - __clz(block_size - 1);
+  int lvl = bits - 10;
+  return lvl < 0 ? 0 : lvl;
+}
+__device__ __forceinline__ uint8_t lz4b_header_byte(int j, int token, uint32_t clen, uint32_t olen, uint32_t check) {
+  const uint64_t magic = 0x6B636F6C42345A4Cull;  // "LZ4Block"
+  if (j < 8) return (uint8_t)(magic >> (8 * j));
+  if (j == 8) return (uint8_t)token;
+  if (j < 13) return (uint8_t)(clen >> (8 * (j - 9)));
+  if (j < 17) return (uint8_t)(olen >> (8 * (j - 13)));
+  return (uint8_t)(check >> (8 * (j - 17)));
+}
+__device__ __forceinline__ void warp_store_len_ext(uint8_t* o, int nb, int r, int lane) {
+  for (int j = lane; j < nb; j += 32) o[j] = (j == nb - 1) ? (uint8_t)(r - 255 * (nb - 1)) : (uint8_t)255;
+}
+// cooperative emit of one sequence (mlen == 0: final literal run without a match part)
+__device__ __forceinline__ void warp_emit_seq(uint8_t* __restrict__ o, const uint8_t* __restrict__ lit_src, int lit,
+                                              int off, int mlen, int lane) {
+  const int ml = mlen - kMinMatch;
+  const int nbL = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+  if (lane == 0) o[0] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mlen ? (ml < 15 ? ml : 15) : 0));
+  if (nbL) warp_store_len_ext(o + 1, nbL, lit - 15, lane);
+  if (lit >= 96) {
+    group_copy<32>(o + 1 + nbL, lit_src, (uint32_t)lit, lane);
+  } else {
+    for (int j = lane; j < lit; j += 32) o[1 + nbL + j] = __ldg(lit_src + j);
+  }
+  if (mlen) {
+    uint8_t* q = o + 1 + nbL + lit;
+    if (lane == 0) q[0] = (uint8_t)off;
+    if (lane == 1) q[1] = (uint8_t)(off >> 8);
+    if (ml >= 15) warp_store_len_ext(q + 2, (ml - 15) / 255 + 1, ml - 15, lane);
+  }
+}
+
+constexpr int kEmitThreads = 256;
+__global__ void __launch_bounds__(kEmitThreads) lz4_emit_kernel(
+    const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
+    const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+    uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ offarr, const uint2* __restrict__ seqarr,
+    const uint32_t* __restrict__ nseq, const uint32_t* __restrict__ csize, const uint32_t* __restrict__ hash,
+    const uint64_t* __restrict__ scan, uint8_t* __restrict__ dst_base, uint64_t dst_cap) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bl = blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5);
+  if (bl >= m) return;
+  const uint32_t b = b0 + bl;
+  const BlockSpan B = block_span(src_base, src_off, src_len, blk_base, n_streams, b, block_size);
+  const uint8_t* __restrict__ s = B.s;
+  const uint32_t cs = csize[b];
+  const bool raw = cs & 0x80000000u;
+  const uint32_t clen = cs & 0x7fffffffu;
+  const uint64_t o0 = scan[b] + 21ull * B.stream;
+  if (o0 + 21ull + clen > dst_cap) return;  // the stream-meta kernel reports B2S_E_DST_TOO_SMALL for this stream
+  uint8_t* __restrict__ o = dst_base + o0;
+  const int token = (raw ? 0x10 : 0x20) | lz4b_level(block_size);
+  if (lane < 21) o[lane] = lz4b_header_byte(lane, token, clen, (uint32_t)B.n, hash[b] & 0x0FFFFFFFu);
+  uint8_t* __restrict__ out = o + 21;
+  if (raw) {
+    group_copy<32>(out, s, clen, lane);
+    return;
+  }
+  const uint32_t ns = nseq[b];
+  const uint2* __restrict__ seq = seqarr + (size_t)bl * max_seq;
+  const uint16_t* __restrict__ offp = offarr + (size_t)bl * stride;
+  for (uint32_t i0 = 0; i0 < ns; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    bool slow = false;
+    int anchor = 0, lit = 0, ml = 0, op = 0, off = 0;
+    if (i < ns) {
+      const uint2 r = seq[i];
+      anchor = (int)(r.x & 0xffffu);
+      lit = (int)(r.x >> 16);
+      ml = (int)(r.y & 0xffffu);
+      op = (int)(r.y >> 16);
+      const int mlc = ml - kMinMatch;
+      if (ml) off = offp[anchor + lit];
+      if (lit <= 16 && ml && mlc < 15 + 510) {
+        uint8_t* q = out + op;
+        *q++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mlc < 15 ? mlc : 15));
+        if (lit >= 15) *q++ = (uint8_t)(lit - 15);
+        const uint8_t* ls = s + anchor;
+        for (int j = 0; j < lit; j++) q[j] = __ldg(ls + j);
+        q += lit;
+        q[0] = (uint8_t)off;
+        q[1] = (uint8_t)(off >> 8);
+        if (mlc >= 15) {
+          int rem = mlc - 15;
+          q += 2;
+          if (rem >= 255) {
+            *q++ = 255;
+            rem -= 255;
+          }
+          *q = (uint8_t)rem;
+        }
+      } else {
+        slow = true;
+      }
+    }
+    unsigned slowmask = __ballot_sync(FULL, slow);
+    while (slowmask) {
+      const int l = __ffs(slowmask) - 1;
+      slowmask &= slowmask - 1;
+      const int a_r = __shfl_sync(FULL, anchor, l);
+      const int lit_r = __shfl_sync(FULL, lit, l);
+      const int ml_r = __shfl_sync(FULL, ml, l);
+      const int op_r = __shfl_sync(FULL, op, l);
+      const int off_r = __shfl_sync(FULL, off, l);
+      warp_emit_seq(out + op_r, s + a_r, lit_r, off_r, ml_r, lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------------
+int g_lz4_hlog = 12;  // B2S_LZ4_HLOG (api.cu reads it once at init); 12 is the specified default
+
+template <int HLOG>
+static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                           const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
+                           uint32_t block_size, uint32_t stride, uint16_t* d_off, uint16_t* d_ml,
+                           unsigned int* d_counter, cudaStream_t st) {
+  const size_t smem = (size_t)kMatchWarps * (2u << HLOG);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(lz4_match_kernel<HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_match_kernel<HLOG>, kMatchWarps * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  uint64_t want = ((uint64_t)m + kMatchWarps - 1) / kMatchWarps;
+  uint64_t grid = (uint64_t)kSMs * per_sm;  // persistent: one wave, warps pull blocks from the counter
+  if (grid > want) grid = want;
+  lz4_match_kernel<HLOG><<<(unsigned)grid, kMatchWarps * 32, smem, st>>>(
+      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, d_off, d_ml, d_counter);
+}
+
+size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size) {
+  const size_t stride = (block_size + 31u) & ~31u;
+  const size_t max_seq = stride / 4 + 2;
+  return (size_t)chunk_blocks * (stride * 4 + max_seq * 8) + 1024;
+}
+
+struct Lz4Ws {
+  uint32_t stride, max_seq;
+  uint16_t *off, *ml;
+  uint2* seq;
+};
+static Lz4Ws carve_ws(uint8_t* d_ws, uint32_t m, uint32_t block_size) {
+  Lz4Ws w;
+  w.stride = (block_size + 31u) & ~31u;
+  w.max_seq = w.stride / 4 + 2;
+  w.off = reinterpret_cast<uint16_t*>(d_ws);
+  w.ml = w.off + (size_t)m * w.stride;
+  w.seq = reinterpret_cast<uint2*>(d_ws + (size_t)m * w.stride * 4);
+  return w;
+}
+
+void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                      const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+                      uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches, cudaEvent_t ev0,
+                      cudaEvent_t ev1) {
+  if (!m) return;
+  const Lz4Ws w = carve_ws(d_ws, m, block_size);
+  cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), st);
+  if (ev0) cudaEventRecord(ev0, st);
+#define B2S_LZ4M(H)                                                                                                  \
+  launch_match_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.off, w.ml, \
+                    d_counter, st)
+  switch (g_lz4_hlog) {
+    case 10: B2S_LZ4M(10); break;
+    case 11: B2S_LZ4M(11); break;
+    case 13: B2S_LZ4M(13); break;
+    default: B2S_LZ4M(12); break;
+  }
+#undef B2S_LZ4M
+  if (ev1) cudaEventRecord(ev1, st);
+  *launches += 1;
+}
+
+void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                           const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
+                           uint32_t block_size, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,
+                           const uint32_t* d_hash, uint64_t* d_sizes, uint64_t* d_running_total, uint64_t* d_scan_ws,
+                           uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches) {
+  if (!m) return;
+  const Lz4Ws w = carve_ws(d_ws, m, block_size);
+  lz4_parse_kernel<<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
+                                                 w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+  // packed offsets of this chunk's blocks, chained onto the running total of the chunks before it
+  launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);
+  lz4_emit_kernel<<<(m + kEmitThreads / 32 - 1) / (kEmitThreads / 32), kEmitThreads, 0, st>>>(
+      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq, w.off, w.seq,
+      d_nseq, d_csize, d_hash, d_sizes, dst_base, dst_cap);
+  *launches += 2;
+}
+
+// per stream: packed offset/length, end mark, capacity check (runs once all chunks have been scanned)
+__global__ void lz4block_stream_meta_kernel(const uint32_t* __restrict__ blk_base, uint32_t n_streams,
+                                            uint32_t n_blocks, uint32_t block_size, const uint64_t* __restrict__ scan,
+                                            const uint64_t* __restrict__ scan_total, uint8_t* __restrict__ dst_base,
+                                            uint64_t dst_cap, uint64_t* __restrict__ dst_off,
+                                            uint64_t* __restrict__ dst_len, int32_t* __restrict__ status) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_streams) return;
+  const uint32_t b0 = blk_base[i], b1 = blk_base[i + 1];
+  const uint64_t s0 = b0 < n_blocks ? scan[b0] : *scan_total;
+  const uint64_t s1 = b1 < n_blocks ? scan[b1] : *scan_total;
+  const uint64_t off = s0 + 21ull * i;
+  const uint64_t len = (s1 - s0) + 21ull;
+  dst_off[i] = off;
+  dst_len[i] = len;
+  if (off + len > dst_cap) {
+    status[i] = B2S_E_DST_TOO_SMALL;
+    return;
+  }
+  uint8_t* e = dst_base + off + len - 21;
+  const int token = 0x10 | lz4b_level(block_size);
+#pragma unroll
+  for (int j = 0; j < 21; j++) e[j] = lz4b_header_byte(j, token, 0, 0, 0);
+}
+
+void launch_lz4block_stream_meta(const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
+                                 const uint64_t* d_scan, const uint64_t* d_scan_total, uint8_t* dst_base,
+                                 uint64_t dst_cap, uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status,
+                                 cudaStream_t st, uint64_t* launches) {
+  if (!n_streams) return;
+  lz4block_stream_meta_kernel<<<(n_streams + 255) / 256, 256, 0, st>>>(d_blk_base, n_streams, n_blocks, block_size,
+                                                                       d_scan, d_scan_total, dst_base, dst_cap,
+                                                                       d_dst_off, d_dst_len, d_status);
+  *launches += 1;
+}
+
+}  // namespace b2s

@@ -1,0 +1,220 @@
+// lz4_decode.cu — K4: LZ4 block decompression as two kernels (LZ4_decompress_fast semantics: driven by originalLen,
+// must consume exactly compressedLen; oracle: orc_lz4_decompress_block).
+//
+// Replaces liblz4's LZ4_decompress_fast as driven by lz4-java's LZ4BlockInputStream [U] under
+// serializerManager.wrapStream at storage/S3ShuffleReader.scala:107-109.
+//
+// Same split as the compressor (lz4_compress.cu): the token chain of a block is inherently serial, the byte copies
+// are not.  The first, single-kernel decoder (kept below in lz4.cu as the path for codec blocks > 64 KiB) carried the
+// serial chain on 8-lane tiles and spent 5.0 warp-instructions per output byte (profiles/r1a).
+//
+//   P1 lz4_tokens_kernel  THREAD per codec block: walks tokens / length bytes / offsets, validates every bound the
+//                         JVM reader would trip over, and writes one 8-byte record per sequence
+//                         (literal count, match length, offset, literal source position).
+//   P2 lz4_copy_kernel    warp per codec block, LANE per sequence: output positions by a warp scan, all literals of a
+//                         batch of 32 sequences copied at once, then the matches in dependency rounds — a match is
+//                         ready when its source lies entirely below the output of the earliest unfinished match;
+//                         short matches are copied by their lanes, long ones by the whole warp.
+#include "kernels.h"
+
+namespace b2s {
+
+constexpr int kMinMatch = 4, kMFLimit = 12, kLastLiterals = 5;
+
+// record: x = literal count | match length << 16 (0 = final sequence) ; y = offset | literal source position << 16
+__global__ void __launch_bounds__(64) lz4_tokens_kernel(const BlockDesc* __restrict__ desc, uint32_t b0, uint32_t m,
+                                                        const uint8_t* __restrict__ src_base, uint2* __restrict__ rec,
+                                                        uint32_t rec_stride, uint32_t* __restrict__ nrec,
+                                                        int32_t* __restrict__ status) {
+  const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= m) return;
+  const uint32_t b = b0 + bl;
+  const BlockDesc d = desc[b];
+  if (d.olen == 0 || (d.stream & 0x80000000u)) {  // no-op descriptor or stored RAW (copied by P2)
+    nrec[b] = 0;
+    return;
+  }
+  const uint8_t* __restrict__ in = src_base + d.src;
+  const int clen = (int)d.clen, olen = (int)d.olen;
+  uint2* __restrict__ r = rec + (size_t)bl * rec_stride;
+  int ip = 0, op = 0;
+  uint32_t ns = 0;
+  bool err = false;
+  if (clen > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + 128));
+  for (;;) {
+    if (ip >= clen) {
+      err = true;
+      break;
+    }
+    if ((ip & 31) < 4 && ip + 256 < clen)  // ~once per 32-byte sector: each lane streams its own block
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(in + ip + 256));
+    const int token = __ldg(in + ip++);
+    int ll = token >> 4;
+    if (ll == 15) {
+      int bb;
+      do {
+        if (ip >= clen) {
+          err = true;
+          break;
+        }
+        bb = __ldg(in + ip++);
+        ll += bb;
+      } while (bb == 255);
+      if (err) break;
+    }
+    if (ll > olen - op || ll > clen - ip) {
+      err = true;
+      break;
+    }
+    const int lit_ip = ip;
+    ip += ll;
+    op += ll;
+    if (olen - op < kMFLimit) {  // last sequence: literals only; a match may not start < 12 bytes before the end
+      if (op != olen || ip != clen) err = true;
+      else r[ns++] = make_uint2((uint32_t)ll, (uint32_t)lit_ip << 16);
+      break;
+    }
+    if (ip + 2 > clen) {
+      err = true;
+      break;
+    }
+    const int off = __ldg(in + ip) | (__ldg(in + ip + 1) << 8);
+    ip += 2;
+    int ml = token & 15;
+    if (ml == 15) {
+      int bb;
+      do {
+        if (ip >= clen) {
+          err = true;
+          break;
+        }
+        bb = __ldg(in + ip++);
+        ml += bb;
+      } while (bb == 255);
+      if (err) break;
+    }
+    ml += kMinMatch;
+    if (ml > olen - op || off == 0 || off > op) {
+      err = true;
+      break;
+    }
+    r[ns++] = make_uint2((uint32_t)ll | ((uint32_t)ml << 16), (uint32_t)off | ((uint32_t)lit_ip << 16));
+    op += ml;
+    if (olen - op < kLastLiterals) {  // the last 5 bytes of a block are literals
+      err = true;
+      break;
+    }
+  }
+  if (err) {
+    set_status(status, d.stream & 0x7fffffffu, B2S_E_CORRUPT);
+    ns = 0;
+  }
+  nrec[b] = ns;
+}
+
+constexpr int kCopyThreads = 256;
+__global__ void __launch_bounds__(kCopyThreads) lz4_copy_kernel(const BlockDesc* __restrict__ desc, uint32_t b0,
+                                                                uint32_t m, const uint8_t* __restrict__ src_base,
+                                                                uint8_t* dst_base, const uint2* __restrict__ rec,
+                                                                uint32_t rec_stride,
+                                                                const uint32_t* __restrict__ nrec) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bl = blockIdx.x * (kCopyThreads / 32) + (threadIdx.x >> 5);
+  if (bl >= m) return;
+  const uint32_t b = b0 + bl;
+  const BlockDesc d = desc[b];
+  if (d.olen == 0) return;
+  const uint8_t* __restrict__ in = src_base + d.src;
+  uint8_t* out = dst_base + d.dst;
+  if (d.stream & 0x80000000u) {
+    group_copy<32>(out, in, d.olen, lane);
+    return;
+  }
+  const uint32_t n = nrec[b];
+  const uint2* __restrict__ r = rec + (size_t)bl * rec_stride;
+  int base_op = 0;
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    uint2 q = make_uint2(0, 0);
+    if (i < n) q = r[i];
+    const int lit = (int)(q.x & 0xffffu), ml = (int)(q.x >> 16);
+    const int off = (int)(q.y & 0xffffu), lip = (int)(q.y >> 16);
+    // output position of every sequence of the batch: exclusive scan of lit + ml
+    int inc = lit + ml;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const int t = __shfl_up_sync(FULL, inc, s);
+      if (lane >= s) inc += t;
+    }
+    const int op = base_op + inc - (lit + ml);
+    base_op += __shfl_sync(FULL, inc, 31);
+
+    // ---- literals: independent of everything, all lanes at once; long runs go through the whole warp
+    if (lit <= 16) {
+      for (int j = 0; j < lit; j++) out[op + j] = __ldg(in + lip + j);
+    }
+    unsigned biglit = __ballot_sync(FULL, lit > 16);
+    while (biglit) {
+      const int l = __ffs(biglit) - 1;
+      biglit &= biglit - 1;
+      const int n_l = __shfl_sync(FULL, lit, l), op_l = __shfl_sync(FULL, op, l), ip_l = __shfl_sync(FULL, lip, l);
+      if (n_l >= 96) group_copy<32>(out + op_l, in + ip_l, (uint32_t)n_l, lane);
+      else
+        for (int j = lane; j < n_l; j += 32) out[op_l + j] = __ldg(in + ip_l + j);
+    }
+    __syncwarp();
+
+    // ---- matches, in dependency rounds
+    const int mdst = op + lit;
+    const int msrc = mdst - off;
+    bool pending = ml > 0;
+    unsigned pendmask = __ballot_sync(FULL, pending);
+    while (pendmask) {
+      const int first = __ffs(pendmask) - 1;                 // earliest unfinished match
+      const int frontier = __shfl_sync(FULL, mdst, first);   // everything below its output is final
+      const bool ready = pending && (lane == first || msrc + ml <= frontier);
+      const unsigned readymask = __ballot_sync(FULL, ready);
+      if (ready && ml <= 16) {
+        // sequential byte copy: also right for an overlapping match (off < ml), which can only be `first`
+        for (int j = 0; j < ml; j++) out[mdst + j] = out[msrc + j];
+      }
+      unsigned longmask = __ballot_sync(FULL, ready && ml > 16);
+      while (longmask) {
+        const int l = __ffs(longmask) - 1;
+        longmask &= longmask - 1;
+        const int ml_l = __shfl_sync(FULL, ml, l), off_l = __shfl_sync(FULL, off, l);
+        uint8_t* o = out + __shfl_sync(FULL, mdst, l);
+        const uint8_t* sp = o - off_l;
+        if (off_l >= ml_l && ml_l >= 96) {
+          group_copy<32>(o, sp, (uint32_t)ml_l, lane);
+        } else {
+          // overlapping match (off < ml): every byte comes from the already complete window [o - off, o)
+          for (int j = lane; j < ml_l; j += 32) o[j] = sp[j >= off_l ? (int)((unsigned)j % (unsigned)off_l) : j];
+        }
+      }
+      pending = pending && !ready;
+      pendmask &= ~readymask;
+      __syncwarp();  // this round's bytes are visible to the next round's loads
+    }
+  }
+}
+
+size_t lz4_decode_ws_bytes(uint32_t chunk_blocks, uint32_t max_olen) {
+  const size_t rec_stride = (size_t)max_olen / 4 + 2;
+  return (size_t)chunk_blocks * rec_stride * 8 + 256;
+}
+
+void launch_lz4_decode_chunk(const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t max_olen,
+                             const uint8_t* src_base, uint8_t* dst_base, uint8_t* d_ws, uint32_t* d_nrec,
+                             int32_t* d_status, cudaStream_t st, uint64_t* launches) {
+  if (!m) return;
+  const uint32_t rec_stride = max_olen / 4 + 2;
+  uint2* rec = reinterpret_cast<uint2*>(d_ws);
+  lz4_tokens_kernel<<<(m + 63) / 64, 64, 0, st>>>(d_desc, b0, m, src_base, rec, rec_stride, d_nrec, d_status);
+  lz4_copy_kernel<<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
+      d_desc, b0, m, src_base, dst_base, rec, rec_stride, d_nrec);
+  *launches += 2;
+}
+
+}  // namespace b2s

@@ -51,10 +51,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint64_
 }
 
 // single CTA: exclusive scan of the partials in place, grand total out
+// (base: optional running offset added to every result; grand may alias base => chained chunk scans)
 __global__ void __launch_bounds__(kScanThreads) scan_partials_kernel(uint64_t* __restrict__ partial, size_t m,
-                                                                     uint64_t* __restrict__ grand) {
+                                                                     uint64_t* grand, const uint64_t* base) {
   __shared__ uint64_t total;
-  uint64_t carry = 0;
+  uint64_t carry = base ? *base : 0;
+  __syncthreads();
   for (size_t base = 0; base < m; base += kScanThreads) {
     size_t i = base + threadIdx.x;
     uint64_t x = i < m ? partial[i] : 0;
@@ -90,14 +92,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint64_t* __re
 size_t scan_ws_elems(size_t n) { return (n + kScanTile - 1) / kScanTile + 1; }
 
 void launch_exclusive_scan_u64(uint64_t* d_v, size_t n, uint64_t* d_total, uint64_t* d_ws, cudaStream_t st,
-                               uint64_t* launches) {
+                               uint64_t* launches, const uint64_t* d_base) {
   if (n == 0) {
-    cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st);
+    if (!d_base) cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st);
+    else if (d_base != d_total) cudaMemcpyAsync(d_total, d_base, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st);
     return;
   }
   const size_t m = (n + kScanTile - 1) / kScanTile;
   scan_reduce_kernel<<<(unsigned)m, kScanThreads, 0, st>>>(d_v, n, d_ws);
-  scan_partials_kernel<<<1, kScanThreads, 0, st>>>(d_ws, m, d_total);
+  scan_partials_kernel<<<1, kScanThreads, 0, st>>>(d_ws, m, d_total, d_base);
   scan_apply_kernel<<<(unsigned)m, kScanThreads, 0, st>>>(d_v, n, d_ws);
   if (launches) *launches += 3;
 }
