@@ -30,6 +30,9 @@ RECORD = 104
 RECORDS_PER_BLOCK = 6453            # 671,112 B per shuffle block
 N_BLOCKS_FULL = 16000               # 80 maps x 200 reduce partitions  => 10.0003 GiB
 LZ4_BLOCK = 32768
+# dram__bytes_read.sum + dram__bytes_write.sum of one lz4_match_kernel launch over a 1.25 GiB chunk (ncu --set full,
+# profiles/r1c_*), scaled to the bench's 1 GiB chunks at run time; None until a capture of the current kernel exists
+NCU_TRAFFIC_PER_LAUNCH = None
 METRIC = "shuffle write+read GB/s (compress+CRC) at 1/2/4/8 B200 vs JVM-LZ4 CPU baseline"
 
 
@@ -219,19 +222,26 @@ def main():
     match_ms = statistics.mean(kt["match_ms"])
     match_launches = max(1, int(statistics.mean(kt["match_launches"])))
     peak, peak_src = measured_peak()
-    # dominant kernel = lz4_match_kernel (phase A of the compressor).  Its algorithmic traffic per launch: read the
-    # chunk's U bytes once, write the per-position match table (off u16 + ml8 u8 = 3 B per input byte) — DESIGN.md §4.
-    alg_bytes = 4.0 * total / match_launches
+    # dominant kernel = lz4_match_kernel (phase A of the compressor; largest share in profiles/*launches*.csv).
+    # achieved = SURVEY §8(d)'s write-step figure (1+r) x the input bytes one launch processes / its launch duration.
+    step_alg = (1.0 + ratio) * total                       # compress step reads U, writes C (= decompress step mirrored)
+    alg_bytes = step_alg / match_launches
     achieved = alg_bytes / (match_ms / match_launches * 1e-3) / 1e9
-    step_alg = (1.0 + ratio) * total                       # compress step reads U, writes C
+    dec_ms = statistics.mean(kt["decompress_ms"])
     roofline = {"bound": "hbm", "kernel": "lz4_match_kernel<12>", "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": NCU_TRAFFIC_PER_LAUNCH,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(match_ms / match_launches, 4),
                 "launches_per_step": match_launches,
-                "compress_step": {"kernels": "match + parse + scan + emit", "algorithmic_bytes": int(step_alg),
-                                  "ms": round(comp_ms, 3), "achieved": round(step_alg / (comp_ms * 1e-3) / 1e9, 2),
+                "compress_step": {"kernels": "lz4_match + lz4_parse + scan + lz4_emit (what one fused kernel would do)",
+                                  "algorithmic_bytes": int(step_alg), "ms": round(comp_ms, 3),
+                                  "achieved": round(step_alg / (comp_ms * 1e-3) / 1e9, 2),
                                   "frac": round(step_alg / (comp_ms * 1e-3) / 1e9 / peak, 5)},
-                "note": "LZ codec kernels are issue/latency bound byte-stream work; frac is honest HBM utilisation"}
+                "decompress_step": {"kernels": "lz4_tokens + lz4_copy", "algorithmic_bytes": int(step_alg),
+                                    "ms": round(dec_ms, 3), "achieved": round(step_alg / (dec_ms * 1e-3) / 1e9, 2),
+                                    "frac": round(step_alg / (dec_ms * 1e-3) / 1e9 / peak, 5)},
+                "note": "LZ77 coding is issue/latency-bound byte-stream work; traffic (ncu dram bytes per launch, "
+                        "profiles/) exceeds the algorithmic bytes by the per-position match table handed to the parse kernel"}
     kernels = {"compress_ms": round(comp_ms, 3), "match_ms": round(match_ms, 3), "decompress_ms": round(statistics.mean(kt["decompress_ms"]), 3),
                "write_pass_kernels_ms": round(statistics.mean(kt["write_kernel_ms"]), 3),
                "read_pass_kernels_ms": round(statistics.mean(kt["read_kernel_ms"]), 3),

@@ -234,26 +234,33 @@ last_literals:
  *     matchlimit; the cursor jumps to its end.
  *  C  LZ4 sequence emission.
  */
-int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap, int hash_log) {
+/* phase A of the GPU model: off[p] for every p <= n - 12 (0 = no match); off has n entries, zero-initialised */
+static void win_find_offsets(const uint8_t* src, int n, int hash_log, uint16_t* off) {
   enum { W = 32 };
-  if (n > 65536 || hash_log > 16 || hash_log < 4) return 0;
   uint16_t* table = (uint16_t*)calloc((size_t)1 << hash_log, sizeof(uint16_t));
+  const int mflimit = n - LZ4_MFLIMIT;
+  for (int pos = 0; pos <= mflimit; pos += W) {
+    const int last = pos + W - 1 < mflimit ? pos + W - 1 : mflimit;
+    for (int p = pos; p <= last; p++) {
+      const uint32_t v = rd32(src + p);
+      const int c = table[lz4_hash(v, hash_log)];
+      if (p > 0 && rd32(src + p - 1) == v) off[p] = 1;
+      else if (c < p && rd32(src + c) == v) off[p] = (uint16_t)(p - c);
+    }
+    for (int p = pos; p <= last; p++) table[lz4_hash(rd32(src + p), hash_log)] = (uint16_t)p;
+  }
+  free(table);
+}
+
+int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap, int hash_log) {
+  if (n > 65536 || hash_log > 16 || hash_log < 4) return 0;
   uint16_t* off = (uint16_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(uint16_t));
   int op = 0, anchor = 0;
   if (n >= LZ4_MFLIMIT + 1) {
     const int mflimit = n - LZ4_MFLIMIT;
     const int matchlimit = n - LZ4_LASTLITERALS;
-    for (int pos = 0; pos <= mflimit; pos += W) { /* phase A */
-      const int last = pos + W - 1 < mflimit ? pos + W - 1 : mflimit;
-      for (int p = pos; p <= last; p++) {
-        const uint32_t v = rd32(src + p);
-        const int c = table[lz4_hash(v, hash_log)];
-        if (p > 0 && rd32(src + p - 1) == v) off[p] = 1;
-        else if (c < p && rd32(src + c) == v) off[p] = (uint16_t)(p - c);
-      }
-      for (int p = pos; p <= last; p++) table[lz4_hash(rd32(src + p), hash_log)] = (uint16_t)p;
-    }
-    int p = 0; /* phase B + C */
+    win_find_offsets(src, n, hash_log, off); /* phase A */
+    int p = 0;                                /* phase B + C */
     while (p <= mflimit) {
       if (!off[p]) {
         p++;
@@ -264,7 +271,6 @@ int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap,
       while (p + mlen < matchlimit && src[p + mlen] == src[c + mlen]) mlen++;
       op = lz4_emit_seq(src, anchor, p - anchor, off[p], mlen, dst, op, cap);
       if (op < 0) {
-        free(table);
         free(off);
         return 0;
       }
@@ -273,7 +279,6 @@ int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap,
     }
   }
   op = lz4_emit_seq(src, anchor, n - anchor, 0, 0, dst, op, cap);
-  free(table);
   free(off);
   return op < 0 ? 0 : op;
 }
@@ -530,6 +535,45 @@ int64_t orc_snappy_compress_raw(const uint8_t* src, uint64_t n, uint8_t* dst, ui
   return (int64_t)op;
 }
 
+/* CPU model of the GPU Snappy compressor: the same match finding and greedy parse as orc_lz4_compress_block_win
+ * (including its end-of-block margins: no match starts in the last 12 bytes or covers the last 5 — legal, merely
+ * conservative, for Snappy), emitted in the Snappy element grammar.  One chunk <= 32 KiB (the xerial block size). */
+int64_t orc_snappy_compress_raw_win(const uint8_t* src, uint64_t n64, uint8_t* dst, uint64_t cap, int hash_log) {
+  if (n64 > 32768 || cap < orc_snappy_max_compressed(n64)) return -2;
+  const int n = (int)n64;
+  uint64_t op = 0;
+  uint64_t v = n64;
+  while (v >= 0x80) {
+    dst[op++] = (uint8_t)(v | 0x80);
+    v >>= 7;
+  }
+  dst[op++] = (uint8_t)v;
+  int anchor = 0;
+  if (n >= LZ4_MFLIMIT + 1) {
+    uint16_t* off = (uint16_t*)calloc((size_t)n, sizeof(uint16_t));
+    const int mflimit = n - LZ4_MFLIMIT;
+    const int matchlimit = n - LZ4_LASTLITERALS;
+    win_find_offsets(src, n, hash_log, off);
+    int p = 0;
+    while (p <= mflimit) {
+      if (!off[p]) {
+        p++;
+        continue;
+      }
+      const int c = p - off[p];
+      int mlen = LZ4_MINMATCH;
+      while (p + mlen < matchlimit && src[p + mlen] == src[c + mlen]) mlen++;
+      if (p > anchor) op = snappy_emit_literal(dst, op, src + anchor, (uint64_t)(p - anchor));
+      op = snappy_emit_copy(dst, op, off[p], (uint32_t)mlen);
+      p += mlen;
+      anchor = p;
+    }
+    free(off);
+  }
+  if (anchor < n) op = snappy_emit_literal(dst, op, src + anchor, (uint64_t)(n - anchor));
+  return (int64_t)op;
+}
+
 int64_t orc_snappy_uncompressed_length(const uint8_t* src, uint64_t n) {
   uint64_t v = 0;
   for (int i = 0; i < 5; i++) {
@@ -607,19 +651,29 @@ uint64_t orc_xerial_bound(uint64_t n, uint32_t block_size) {
   uint64_t nb = (n + block_size - 1) / block_size;
   return ORC_XERIAL_HEADER + nb * (4 + orc_snappy_max_compressed(block_size));
 }
-int64_t orc_xerial_compress(const uint8_t* src, uint64_t n, uint32_t block_size, uint8_t* dst, uint64_t cap) {
+static int64_t xerial_compress_impl(const uint8_t* src, uint64_t n, uint32_t block_size, uint8_t* dst, uint64_t cap,
+                                    int compressor) {
   if (cap < ORC_XERIAL_HEADER) return -2;
   memcpy(dst, XERIAL_HEADER, 16);
   uint64_t op = 16;
   for (uint64_t off = 0; off < n; off += block_size) {
     uint64_t o = n - off < block_size ? n - off : block_size;
     if (op + 4 + orc_snappy_max_compressed(o) > cap) return -2;
-    int64_t c = orc_snappy_compress_raw(src + off, o, dst + op + 4, cap - op - 4);
+    int64_t c = compressor == 1 ? orc_snappy_compress_raw_win(src + off, o, dst + op + 4, cap - op - 4, 12)
+                                : orc_snappy_compress_raw(src + off, o, dst + op + 4, cap - op - 4);
     if (c < 0) return c;
     wr_be32(dst + op, (uint32_t)c);
     op += 4 + (uint64_t)c;
   }
   return (int64_t)op;
+}
+int64_t orc_xerial_compress(const uint8_t* src, uint64_t n, uint32_t block_size, uint8_t* dst, uint64_t cap) {
+  return xerial_compress_impl(src, n, block_size, dst, cap, 0);
+}
+/* compressor: 0 = restated snappy-style greedy, 1 = GPU window model (hash_log 12, block_size <= 32 KiB) */
+int64_t orc_xerial_compress2(const uint8_t* src, uint64_t n, uint32_t block_size, uint8_t* dst, uint64_t cap,
+                             int compressor) {
+  return xerial_compress_impl(src, n, block_size, dst, cap, compressor);
 }
 static int64_t xerial_walk(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap) {
   if (n < 16 || memcmp(src, XERIAL_HEADER, 8)) return -1;

@@ -70,6 +70,8 @@ def lib():
         L.orc_xerial_bound.argtypes = [C.c_uint64, C.c_uint32]
         L.orc_xerial_compress.restype = C.c_int64
         L.orc_xerial_compress.argtypes = [u8p, C.c_uint64, C.c_uint32, u8p, C.c_uint64]
+        L.orc_xerial_compress2.restype = C.c_int64
+        L.orc_xerial_compress2.argtypes = [u8p, C.c_uint64, C.c_uint32, u8p, C.c_uint64, C.c_int]
         L.orc_xerial_decompress.restype = C.c_int64
         L.orc_xerial_decompress.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64]
         L.orc_xerial_decompressed_size.restype = C.c_int64
@@ -200,11 +202,12 @@ def snappy_uncompress_raw(b):
     return out[:r].tobytes()
 
 
-def xerial_compress(b, block_size=32768):
+def xerial_compress(b, block_size=32768, compressor=0):
+    """compressor: 0 = restated snappy-style greedy, 1 = CPU model of the GPU compressor"""
     a = _u8(b)
     cap = lib().orc_xerial_bound(a.size, block_size)
     out = np.empty(cap, dtype=np.uint8)
-    n = lib().orc_xerial_compress(_p(a), a.size, block_size, out.ctypes.data, cap)
+    n = lib().orc_xerial_compress2(_p(a), a.size, block_size, out.ctypes.data, cap, compressor)
     if n < 0:
         raise ValueError("xerial compress failed")
     return out[:n].tobytes()

@@ -46,8 +46,8 @@ constexpr int NSLOT = 3;
 constexpr uint64_t kChunkBytes = 64ull << 20;
 constexpr uint32_t kChunkStreams = 1u << 18;
 constexpr uint32_t kXxhSeed = 0x9747b28cu;
-uint32_t g_lz4_chunk_blocks = 32768;
-int g_lz4d_legacy = 0;  // B2S_LZ4D_LEGACY=1: single-kernel tile decoder for every block size (A/B comparisons)  // codec blocks per match/parse/emit pass (bounds the workspace); B2S_LZ4_CHUNK_BLOCKS
+uint32_t g_lz4_chunk_blocks = 32768;  // codec blocks per match/parse/emit (or tokens/copy) pass: bounds the workspace; B2S_LZ4_CHUNK_BLOCKS
+int g_lz4d_legacy = 0;  // B2S_LZ4D_LEGACY=1: single-kernel tile decoder for every block size (A/B comparisons)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -192,8 +192,11 @@ struct WallTimer {
 // --------------------------------------------------------------------------------------------------------------
 // compress job: one chunk of n streams living in a device source arena
 // --------------------------------------------------------------------------------------------------------------
+// bytes every stream adds around its codec blocks: LZ4Block end mark (21) / xerial stream header (16)
+inline uint64_t stream_overhead(uint32_t codec) { return codec == B2S_CODEC_SNAPPY_XERIAL ? 16ull : 21ull; }
+
 struct CompressJob {
-  uint32_t n = 0, nb = 0;
+  uint32_t n = 0, nb = 0, codec = 0;
   // pinned host mirror
   uint64_t *h_src_off = nullptr, *h_src_len = nullptr;
   uint32_t* h_blk_base = nullptr;
@@ -206,9 +209,14 @@ struct CompressJob {
 
 // lays out pinned + device meta for a compress chunk; returns 0 or error
 int compress_prepare(Slot& S, uint32_t codec, uint32_t bs, uint32_t n, const uint64_t* src_len, CompressJob& J) {
-  if (codec != B2S_CODEC_LZ4BLOCK) return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", "");
-  if (bs < 64 || bs > 65536) return fail(B2S_E_UNSUPPORTED, "lz4 block size must be in [64, 65536]%s");
+  if (codec != B2S_CODEC_LZ4BLOCK && codec != B2S_CODEC_SNAPPY_XERIAL)
+    return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", codec == B2S_CODEC_ZSTD ? "zstd" : "");
+  if (codec == B2S_CODEC_LZ4BLOCK && (bs < 64 || bs > 65536))
+    return fail(B2S_E_UNSUPPORTED, "lz4 block size must be in [64, 65536]%s");
+  if (codec == B2S_CODEC_SNAPPY_XERIAL && (bs < 64 || bs > 32768))
+    return fail(B2S_E_UNSUPPORTED, "snappy block size must be in [64, 32768]%s");
   J.n = n;
+  J.codec = codec;
   uint64_t nb = 0;
   for (uint32_t i = 0; i < n; i++) nb += (src_len[i] + bs - 1) / bs;
   if (nb >= 0x7fffffffull) return fail(B2S_E_ARG, "too many codec blocks in one chunk%s");
@@ -291,7 +299,9 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
   CU(cudaMemcpyAsync(J.d_up, J.h_up, J.up_bytes, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(J.d_down, 0, J.down_bytes, st));
   CU(cudaEventRecord(S.ev_k0, st));
-  launch_xxh32_encode(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, kXxhSeed, M.hash, st, launches);
+  const uint32_t codec = J.codec;
+  if (codec == B2S_CODEC_LZ4BLOCK)
+    launch_xxh32_encode(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, kXxhSeed, M.hash, st, launches);
   CU(cudaEventRecord(S.ev_t0, st));
   CU(cudaMemsetAsync(M.total, 0, 16, st));
   // Chunks of `chunk` codec blocks.  The match kernel (issue bound, shared-memory limited) of chunk k+1 runs on the
@@ -307,17 +317,21 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     S.dom_pair(&e0, &e1);
     if (k >= 2) CU(cudaStreamWaitEvent(S.st2, S.ev_free[par], 0));  // emit of chunk k-2 has released this workspace
-    launch_lz4_match(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, ws, M.counter + par, S.st2, launches, e0,
-                     e1);
+    launch_lz4_match(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, codec, ws, M.counter + par, S.st2, launches,
+                     e0, e1);
     CU(cudaEventRecord(S.ev_match[par], S.st2));
     CU(cudaStreamWaitEvent(st, S.ev_match[par], 0));
-    launch_lz4_parse_emit(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, ws, M.nseq, M.csize, M.hash, M.sizes,
-                          M.total, M.ws, d_dst, dst_cap, st, launches);
+    launch_lz4_parse_emit(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, codec, ws, M.nseq, M.csize, M.hash,
+                          M.sizes, M.total, M.ws, d_dst, dst_cap, st, launches);
     CU(cudaEventRecord(S.ev_free[par], st));
   }
   CU(cudaEventRecord(S.ev_t1, st));
-  launch_lz4block_stream_meta(M.blk_base, n, nb, bs, M.sizes, M.total, d_dst, dst_cap, M.dst_off, M.dst_len, M.status,
-                              st, launches);
+  if (codec == B2S_CODEC_SNAPPY_XERIAL)
+    launch_xerial_stream_meta(M.blk_base, n, nb, M.sizes, M.total, d_dst, dst_cap, M.dst_off, M.dst_len, M.status, st,
+                              launches);
+  else
+    launch_lz4block_stream_meta(M.blk_base, n, nb, bs, M.sizes, M.total, d_dst, dst_cap, M.dst_off, M.dst_len,
+                                M.status, st, launches);
   if (alg != B2S_CHECKSUM_NONE) {
     uint32_t shift = pick_tile_shift(dst_cap < (uint64_t)nb * bs ? dst_cap : (uint64_t)nb * bs);
     launch_checksum(tabs, alg, d_dst, M.dst_off, M.dst_len, n, shift, M.work_base, M.ws, M.cks, st, launches);
@@ -334,7 +348,7 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
 // decompress job
 // --------------------------------------------------------------------------------------------------------------
 struct DecompressJob {
-  uint32_t n = 0, n_slices = 0;
+  uint32_t n = 0, n_slices = 0, codec = 0;
   uint64_t nb = 0, total_out = 0;
   uint64_t *h_src_off = nullptr, *h_src_len = nullptr;
   uint64_t *h_slice_off = nullptr, *h_slice_len = nullptr, *h_slice_sum = nullptr;
@@ -354,8 +368,10 @@ struct DecompressJob {
 };
 
 int decompress_prepare(Slot& S, uint32_t codec, uint32_t alg, uint32_t n, uint32_t n_slices, DecompressJob& J) {
-  if (codec != B2S_CODEC_LZ4BLOCK) return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", "");
+  if (codec != B2S_CODEC_LZ4BLOCK && codec != B2S_CODEC_SNAPPY_XERIAL)
+    return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", codec == B2S_CODEC_ZSTD ? "zstd" : "");
   J.n = n;
+  J.codec = codec;
   J.n_slices = alg ? n_slices : 0;
   const uint32_t s = J.n_slices;
   size_t up = align_up(n * 8, 16) * 2 + align_up((size_t)s * 8, 16) * 3 + align_up((size_t)s * 4, 16) +
@@ -427,7 +443,10 @@ int decompress_enqueue_a(Slot& S, const ChecksumTables& tabs, uint32_t alg, Deco
                     J.cks_got, st, launches);
     launch_checksum_compare(J.cks_got, J.slice_sum, J.slice_owner, J.slice_base, s, J.status, J.bad, st, launches);
   }
-  launch_lz4block_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.totals + 2, J.status, st, launches);
+  if (J.codec == B2S_CODEC_SNAPPY_XERIAL)
+    launch_xerial_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.totals + 2, J.status, st, launches);
+  else
+    launch_lz4block_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.totals + 2, J.status, st, launches);
   // dst_off = exclusive scan(olen) ; blk_base = exclusive scan(nblk) (in place)
   CU(cudaMemcpyAsync(J.dst_off, J.olen, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
   launch_exclusive_scan_u64(J.dst_off, n, J.totals + 1, J.ws, st, launches);
@@ -449,15 +468,23 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
   cudaStream_t st = S.st;
   BlockDesc* desc = (BlockDesc*)S.desc.p;
   CU(cudaMemsetAsync(desc, 0, (size_t)J.nb * sizeof(BlockDesc), st));
-  launch_lz4block_fill(d_src, J.src_off, J.src_len, J.n, J.nblk, J.dst_off, J.olen, dst_cap, J.status, desc, st,
+  if (J.codec == B2S_CODEC_SNAPPY_XERIAL)
+    launch_xerial_fill(d_src, J.src_off, J.src_len, J.n, J.nblk, J.dst_off, J.olen, dst_cap, J.status, desc, st,
                        launches);
+  else
+    launch_lz4block_fill(d_src, J.src_off, J.src_len, J.n, J.nblk, J.dst_off, J.olen, dst_cap, J.status, desc, st,
+                         launches);
   CU(cudaEventRecord(S.ev_t0, st));
   const uint64_t max_olen = J.h_totals[2], max_clen = J.h_totals[3];
-  if (J.nb && max_olen <= 65536 && max_clen < 65536 && !g_lz4d_legacy) {
+  const bool small_blocks = max_olen <= 65536 && max_clen < 65536;
+  if (J.codec == B2S_CODEC_SNAPPY_XERIAL && !small_blocks)
+    return fail(B2S_E_UNSUPPORTED, "snappy chunks larger than 64 KiB are not supported%s");
+  if (J.nb && small_blocks && (J.codec == B2S_CODEC_SNAPPY_XERIAL || !g_lz4d_legacy)) {
     // tokens (thread per block) + copy (lane per sequence), in chunks that bound the record workspace
     const uint32_t nb = (uint32_t)J.nb;
+    const uint32_t rec_stride = lz4_decode_rec_stride(J.codec, (uint32_t)max_olen, (uint32_t)max_clen);
     const uint32_t chunk = std::min<uint32_t>(nb, g_lz4_chunk_blocks);
-    rc = S.scratch.ensure(lz4_decode_ws_bytes(chunk, (uint32_t)max_olen) + align_up((size_t)nb * 4, 256));
+    rc = S.scratch.ensure(lz4_decode_ws_bytes(chunk, rec_stride) + align_up((size_t)nb * 4, 256));
     if (rc) return rc;
     uint32_t* nrec = (uint32_t*)S.scratch.p;
     uint8_t* ws = (uint8_t*)S.scratch.p + align_up((size_t)nb * 4, 256);
@@ -465,15 +492,16 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       S.dom_pair(&e0, &e1);
       CU(cudaEventRecord(e0, st));
-      launch_lz4_decode_chunk(desc, b0, std::min<uint32_t>(chunk, nb - b0), (uint32_t)max_olen, d_src, d_dst, ws, nrec,
+      launch_lz4_decode_chunk(J.codec, desc, b0, std::min<uint32_t>(chunk, nb - b0), rec_stride, d_src, d_dst, ws, nrec,
                               J.status, st, launches);
       CU(cudaEventRecord(e1, st));
     }
-  } else {
+  } else if (J.nb) {
     launch_lz4_decompress(desc, (uint32_t)J.nb, d_src, d_dst, J.status, J.counter, st, launches);
   }
   CU(cudaEventRecord(S.ev_t1, st));
-  launch_xxh32_verify(desc, (uint32_t)J.nb, d_dst, kXxhSeed, 0x0FFFFFFFu, J.status, st, launches);
+  if (J.codec == B2S_CODEC_LZ4BLOCK)
+    launch_xxh32_verify(desc, (uint32_t)J.nb, d_dst, kXxhSeed, 0x0FFFFFFFu, J.status, st, launches);
   CU(cudaEventRecord(S.ev_k1, st));
   CU(cudaMemcpyAsync(J.h_down, J.d_down, J.down_bytes, cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(S.ev_b, st));
@@ -669,7 +697,7 @@ uint64_t b2s_compress_bound(uint32_t codec, uint32_t codec_block_size, uint64_t 
   const uint64_t nb = (src_len + bs - 1) / bs;
   switch (codec) {
     case B2S_CODEC_LZ4BLOCK: return src_len + (nb + 1) * 21;  // RAW fallback bounds every block by its input
-    case B2S_CODEC_SNAPPY_XERIAL: return 16 + nb * (4 + 32 + bs + bs / 6);
+    case B2S_CODEC_SNAPPY_XERIAL: return 16 + nb * 37 + src_len + src_len / 6;  // per chunk: BE32 + 32 + n + n/6
     case B2S_CODEC_ZSTD: return src_len + (src_len >> 8) + 64 + nb * 32;
     default: return src_len;
   }
@@ -870,7 +898,7 @@ int b2s_compress_dev(uint32_t dev_index, uint32_t codec, int32_t level, uint32_t
     if (checksum_alg) memcpy(checksum_out, J.h_cks, (size_t)n * 8);
     else memset(checksum_out, 0, (size_t)n * 8);
   }
-  uint64_t total = J.h_total[0] + 21ull * n, srcb = 0;
+  uint64_t total = J.h_total[0] + stream_overhead(codec) * n, srcb = 0;
   for (uint32_t i = 0; i < n; i++) srcb += src_len[i];
   if (dst_total) *dst_total = total;
   add_timing(S, false);
@@ -910,7 +938,7 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
     const uint32_t i0 = starts[c];
     CU(cudaEventSynchronize(S.ev_a));
     add_timing(S, true);
-    const uint64_t chunk_total = J.h_total[0] + 21ull * J.n;
+    const uint64_t chunk_total = J.h_total[0] + stream_overhead(codec) * J.n;
     for (uint32_t k = 0; k < J.n; k++) {
       status[i0 + k] = J.h_status[k];
       dst_len[i0 + k] = J.h_dst_len[k];

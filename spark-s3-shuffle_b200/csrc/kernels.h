@@ -53,11 +53,11 @@ size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size);
 // bytes (bit 31 = stored RAW).
 void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                       const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
-                      uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches, cudaEvent_t ev0,
-                      cudaEvent_t ev1);
+                      uint32_t codec, uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches,
+                      cudaEvent_t ev0, cudaEvent_t ev1);
 void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                            const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
-                           uint32_t block_size, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,
+                           uint32_t block_size, uint32_t codec, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,
                            const uint32_t* d_hash, uint64_t* d_sizes, uint64_t* d_running_total, uint64_t* d_scan_ws,
                            uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches);
 // per stream: dst_off/dst_len, end mark, B2S_E_DST_TOO_SMALL (d_scan = packed block offsets, d_scan_total = their sum)
@@ -79,13 +79,33 @@ void launch_lz4block_fill(const uint8_t* src_base, const uint64_t* d_src_off, co
 void launch_lz4_decompress(const BlockDesc* d_desc, uint32_t n_blocks, const uint8_t* src_base, uint8_t* dst_base,
                            int32_t* d_status, unsigned int* d_counter, cudaStream_t st, uint64_t* launches);
 
-// ---------------- lz4_decode.cu (K4: tokens + copy; codec blocks <= 64 KiB) ----------------
-size_t lz4_decode_ws_bytes(uint32_t chunk_blocks, uint32_t max_olen);
+// ---------------- lz4_decode.cu (K4: tokens + copy; codec blocks <= 64 KiB; the copy kernel also serves Snappy) ------
+uint32_t lz4_decode_rec_stride(uint32_t codec, uint32_t max_olen, uint32_t max_clen);
+size_t lz4_decode_ws_bytes(uint32_t chunk_blocks, uint32_t rec_stride);
 // decodes codec blocks [b0, b0+m): per-sequence records into d_ws, then the byte copies; d_nrec is indexed by global
 // block id.  Malformed blocks set status[stream] = B2S_E_CORRUPT.
-void launch_lz4_decode_chunk(const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t max_olen,
+void launch_lz4_decode_chunk(uint32_t codec, const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t rec_stride,
                              const uint8_t* src_base, uint8_t* dst_base, uint8_t* d_ws, uint32_t* d_nrec,
                              int32_t* d_status, cudaStream_t st, uint64_t* launches);
+
+// ---------------- snappy.cu (K5: xerial framing, Snappy emit / tokens; match, parse and copy kernels are shared) ------
+void launch_snappy_emit(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                        const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+                        uint32_t stride, uint32_t max_seq, const uint16_t* d_off, const uint2* d_seq,
+                        const uint32_t* d_nseq, const uint32_t* d_csize, const uint64_t* d_scan, uint8_t* dst_base,
+                        uint64_t dst_cap, cudaStream_t st, uint64_t* launches);
+void launch_xerial_stream_meta(const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, const uint64_t* d_scan,
+                               const uint64_t* d_scan_total, uint8_t* dst_base, uint64_t dst_cap, uint64_t* d_dst_off,
+                               uint64_t* d_dst_len, int32_t* d_status, cudaStream_t st, uint64_t* launches);
+void launch_xerial_count(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
+                         uint64_t* d_nblk, uint64_t* d_olen, uint64_t* d_maxima, int32_t* d_status, cudaStream_t st,
+                         uint64_t* launches);
+void launch_xerial_fill(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
+                        const uint64_t* d_blk_base, const uint64_t* d_dst_off, uint64_t* d_olen, uint64_t dst_cap,
+                        int32_t* d_status, BlockDesc* d_desc, cudaStream_t st, uint64_t* launches);
+void launch_snappy_tokens(const BlockDesc* d_desc, uint32_t b0, uint32_t m, const uint8_t* src_base, uint2* d_rec,
+                          uint32_t rec_stride, uint32_t* d_nrec, int32_t* d_status, cudaStream_t st,
+                          uint64_t* launches);
 
 // ---------------- gen.cu (bench utility) ----------------
 void launch_gen_terasort(uint8_t* d_dst, uint64_t first_record, uint64_t n_records, uint64_t seed, cudaStream_t st);

@@ -76,7 +76,7 @@ template <int HLOG>
 __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match_kernel(
     const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
     const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
-    uint32_t stride, uint16_t* __restrict__ offarr, uint16_t* __restrict__ mlarr,
+    uint32_t stride, uint32_t near_limit, uint16_t* __restrict__ offarr, uint16_t* __restrict__ mlarr,
     unsigned int* __restrict__ work_counter) {
   extern __shared__ __align__(16) uint16_t smem_tables[];
   constexpr unsigned FULL = 0xffffffffu;
@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match_kernel(
       carry_off = __shfl_sync(FULL, off, 0);
       carry_L = __shfl_sync(FULL, L, 0);
       __stcs(oq, (uint16_t)off);  // position < stride always (stride = block_size rounded up to 32)
-      __stcs(mq, (uint16_t)L);
+      // Snappy (near_limit = 2048, blocks <= 32 KiB so L < 2^15): bit 15 tells the parse kernel that the offset fits
+      // the 2-byte copy element, sparing it a dependent load of off[]
+      __stcs(mq, (uint16_t)(L | (off - 1u < near_limit - 1u ? 0x8000 : 0)));
       oq += 32;
       mq += 32;
     };
@@ -263,6 +265,8 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match_kernel(
 // The walk is a fixed-trip loop over groups of 4 positions (one 64-bit load of ml[], next group prefetched).  A match
 // is at least 4 long, so at most one sequence starts per group: every iteration is the same straight-line code for
 // all 32 lanes (= 32 blocks), no source access, no data-dependent trip counts.
+// SNAPPY = true: same walk, Snappy element sizes (no RAW fallback, varint preamble, copies split at 64 bytes).
+template <bool SNAPPY>
 __global__ void __launch_bounds__(64) lz4_parse_kernel(
     const uint64_t* __restrict__ src_len, const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0,
     uint32_t m, uint32_t block_size, uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ mlarr,
@@ -274,11 +278,12 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
   const uint32_t si = find_stream_of_block(blk_base, n_streams, b);
   const uint64_t rem = src_len[si] - (uint64_t)(b - blk_base[si]) * block_size;
   const int n = (int)(rem < block_size ? rem : block_size);
-  const int cap = n - 1;  // LZ4BlockOutputStream stores RAW when compressedLength >= originalLength
+  // LZ4BlockOutputStream stores RAW when compressedLength >= originalLength; SnappyOutputStream never does
+  const int cap = SNAPPY ? 0x7fffffff : n - 1;
   const unsigned long long* __restrict__ mlw =
       reinterpret_cast<const unsigned long long*>(mlarr + (size_t)bl * stride);
   uint2* __restrict__ seq = seqarr + (size_t)bl * max_seq;
-  int p = 0, anchor = 0, op = 0;
+  int p = 0, anchor = 0, op = SNAPPY ? (n < 128 ? 1 : n < 16384 ? 2 : 3) : 0;  // Snappy: varint(n) comes first
   uint32_t ns = 0;
   bool fail = false;
   const int mflimit = n - kMFLimit;
@@ -297,12 +302,29 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
         if (w) {
           const int bit = (__ffsll((long long)w) - 1) & ~15;
           p += bit >> 4;
-          const int ml = (int)((w >> bit) & 0xffffu);
+          const int mlw16 = (int)((w >> bit) & 0xffffu);
+          const int ml = SNAPPY ? (mlw16 & 0x7fff) : mlw16;
           const int lit = p - anchor;
-          const int mlc = ml - kMinMatch;
-          int size = 3 + lit;
-          if (lit >= 15) size += (lit - 15) / 255 + 1;
-          if (mlc >= 15) size += (mlc - 15) / 255 + 1;
+          int size;
+          if (SNAPPY) {
+            size = lit ? lit + (lit - 1 < 60 ? 1 : lit - 1 < 256 ? 2 : 3) : 0;
+            int len = ml;
+            if (len >= 68) {
+              const int k = (len - 68) / 64 + 1;
+              size += 3 * k;
+              len -= 64 * k;
+            }
+            if (len > 64) {
+              size += 3;
+              len -= 60;
+            }
+            size += (len < 12 && (mlw16 & 0x8000)) ? 2 : 3;
+          } else {
+            const int mlc = ml - kMinMatch;
+            size = 3 + lit;
+            if (lit >= 15) size += (lit - 15) / 255 + 1;
+            if (mlc >= 15) size += (mlc - 15) / 255 + 1;
+          }
           if (op + size > cap) {
             fail = true;
             break;
@@ -316,6 +338,17 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
         }
       }
     }
+  }
+  if (SNAPPY) {
+    const int lit = n - anchor;
+    if (lit) {
+      seq[ns++] = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)op << 16);
+      op += lit + (lit - 1 < 60 ? 1 : lit - 1 < 256 ? 2 : 3);
+    }
+    nseq[b] = ns;
+    csize[b] = (uint32_t)op;
+    sizes[b] = 4u + (uint64_t)op;  // BE32 chunk length + raw snappy block
+    return;
   }
   if (!fail) {
     const int lit = n - anchor;
@@ -457,8 +490,8 @@ int g_lz4_hlog = 12;  // B2S_LZ4_HLOG (api.cu reads it once at init); 12 is the 
 template <int HLOG>
 static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                            const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
-                           uint32_t block_size, uint32_t stride, uint16_t* d_off, uint16_t* d_ml,
-                           unsigned int* d_counter, cudaStream_t st) {
+                           uint32_t block_size, uint32_t stride, uint32_t near_limit, uint16_t* d_off,
+                           uint16_t* d_ml, unsigned int* d_counter, cudaStream_t st) {
   const size_t smem = (size_t)kMatchWarps * (2u << HLOG);
   static bool attr_set = false;
   if (!attr_set) {
@@ -472,7 +505,8 @@ static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, c
   uint64_t grid = (uint64_t)kSMs * per_sm;  // persistent: one wave, warps pull blocks from the counter
   if (grid > want) grid = want;
   lz4_match_kernel<HLOG><<<(unsigned)grid, kMatchWarps * 32, smem, st>>>(
-      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, d_off, d_ml, d_counter);
+      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, near_limit, d_off, d_ml,
+      d_counter);
 }
 
 size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size) {
@@ -498,15 +532,16 @@ static Lz4Ws carve_ws(uint8_t* d_ws, uint32_t m, uint32_t block_size) {
 
 void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                       const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
-                      uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches, cudaEvent_t ev0,
-                      cudaEvent_t ev1) {
+                      uint32_t codec, uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches,
+                      cudaEvent_t ev0, cudaEvent_t ev1) {
   if (!m) return;
+  const uint32_t near_limit = codec == B2S_CODEC_SNAPPY_XERIAL ? 2048u : 0u;
   const Lz4Ws w = carve_ws(d_ws, m, block_size);
   cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), st);
   if (ev0) cudaEventRecord(ev0, st);
 #define B2S_LZ4M(H)                                                                                                  \
-  launch_match_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.off, w.ml, \
-                    d_counter, st)
+  launch_match_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, near_limit, \
+                    w.off, w.ml, d_counter, st)
   switch (g_lz4_hlog) {
     case 10: B2S_LZ4M(10); break;
     case 11: B2S_LZ4M(11); break;
@@ -520,13 +555,22 @@ void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const 
 
 void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                            const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
-                           uint32_t block_size, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,
+                           uint32_t block_size, uint32_t codec, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,
                            const uint32_t* d_hash, uint64_t* d_sizes, uint64_t* d_running_total, uint64_t* d_scan_ws,
                            uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches) {
   if (!m) return;
   const Lz4Ws w = carve_ws(d_ws, m, block_size);
-  lz4_parse_kernel<<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
-                                                 w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+  if (codec == B2S_CODEC_SNAPPY_XERIAL) {
+    lz4_parse_kernel<true><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
+                                                         w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+    launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);
+    launch_snappy_emit(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq,
+                       w.off, w.seq, d_nseq, d_csize, d_sizes, dst_base, dst_cap, st, launches);
+    *launches += 1;
+    return;
+  }
+  lz4_parse_kernel<false><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
+                                                        w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
   // packed offsets of this chunk's blocks, chained onto the running total of the chunks before it
   launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);
   lz4_emit_kernel<<<(m + kEmitThreads / 32 - 1) / (kEmitThreads / 32), kEmitThreads, 0, st>>>(

@@ -200,18 +200,26 @@ __global__ void __launch_bounds__(kCopyThreads) lz4_copy_kernel(const BlockDesc*
   }
 }
 
-size_t lz4_decode_ws_bytes(uint32_t chunk_blocks, uint32_t max_olen) {
-  const size_t rec_stride = (size_t)max_olen / 4 + 2;
+// records per codec block: an LZ4 sequence takes >= 3 compressed bytes and (all but the last) >= 4 output bytes; a
+// Snappy element takes >= 2 compressed bytes and may produce a single byte
+uint32_t lz4_decode_rec_stride(uint32_t codec, uint32_t max_olen, uint32_t max_clen) {
+  if (codec == B2S_CODEC_SNAPPY_XERIAL) return max_clen / 2 + 2;
+  const uint32_t a = max_olen / 4 + 2, b = max_clen / 3 + 2;
+  return a < b ? a : b;
+}
+size_t lz4_decode_ws_bytes(uint32_t chunk_blocks, uint32_t rec_stride) {
   return (size_t)chunk_blocks * rec_stride * 8 + 256;
 }
 
-void launch_lz4_decode_chunk(const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t max_olen,
+void launch_lz4_decode_chunk(uint32_t codec, const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t rec_stride,
                              const uint8_t* src_base, uint8_t* dst_base, uint8_t* d_ws, uint32_t* d_nrec,
                              int32_t* d_status, cudaStream_t st, uint64_t* launches) {
   if (!m) return;
-  const uint32_t rec_stride = max_olen / 4 + 2;
   uint2* rec = reinterpret_cast<uint2*>(d_ws);
-  lz4_tokens_kernel<<<(m + 63) / 64, 64, 0, st>>>(d_desc, b0, m, src_base, rec, rec_stride, d_nrec, d_status);
+  if (codec == B2S_CODEC_SNAPPY_XERIAL)
+    launch_snappy_tokens(d_desc, b0, m, src_base, rec, rec_stride, d_nrec, d_status, st, launches);
+  else
+    lz4_tokens_kernel<<<(m + 63) / 64, 64, 0, st>>>(d_desc, b0, m, src_base, rec, rec_stride, d_nrec, d_status);
   lz4_copy_kernel<<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
       d_desc, b0, m, src_base, dst_base, rec, rec_stride, d_nrec);
   *launches += 2;

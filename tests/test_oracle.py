@@ -198,3 +198,24 @@ def test_cpu_baseline_driver_roundtrips(oracle):
     for use in (True, False):
         r = oracle.baseline_run(data, 65520, threads=4, use_liblz4=use)
         assert r["rc"] == 0 and r["errors"] == 0 and 0.3 < r["compressed_bytes"] / r["bytes"] < 0.7
+
+
+def test_snappy_window_model_is_valid_snappy(oracle):
+    """The CPU model of the GPU Snappy compressor (orc_snappy_compress_raw_win via xerial_compress(compressor=1))
+    emits streams that the restated reader AND the real snappy library (pyarrow) decode."""
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("snappy")
+    for kind in KINDS:
+        for n in (0, 1, 12, 13, 64, 1000, 32768, 32769, 100000):
+            x = corpus(oracle, kind, n, seed=n % 7)
+            s = oracle.xerial_compress(x, 32768, compressor=1)
+            assert oracle.xerial_decompress(s) == x
+            ip = 16
+            out = b""
+            while ip < len(s):
+                clen = int.from_bytes(s[ip:ip + 4], "big")
+                chunk = s[ip + 4:ip + 4 + clen]
+                ulen = min(32768, n - len(out))
+                out += codec.decompress(chunk, decompressed_size=ulen).to_pybytes()
+                ip += 4 + clen
+            assert out == x
