@@ -285,6 +285,8 @@ def main():
                "d2h_bytes_per_step": int(tw["d2h_bytes"] + tr["d2h_bytes"]),
                "ms_per_step": round(e_elapsed / args.e2e_steps * 1e3, 2), "steps": args.e2e_steps,
                "write_ms": round(tw["total_ms"], 2), "read_ms": round(tr["total_ms"], 2),
+               "write_sums_ms": {k: round(tw[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
+               "read_sums_ms": {k: round(tr[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
                "api": "b2s_compress_packed + b2s_decompress_packed on pinned host arenas (b2s_host_alloc)"}
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1)

@@ -368,8 +368,8 @@ struct DecompressJob {
 };
 
 int decompress_prepare(Slot& S, uint32_t codec, uint32_t alg, uint32_t n, uint32_t n_slices, DecompressJob& J) {
-  if (codec != B2S_CODEC_LZ4BLOCK && codec != B2S_CODEC_SNAPPY_XERIAL)
-    return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", codec == B2S_CODEC_ZSTD ? "zstd" : "");
+  if (codec != B2S_CODEC_LZ4BLOCK && codec != B2S_CODEC_SNAPPY_XERIAL && codec != B2S_CODEC_ZSTD)
+    return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", "");
   J.n = n;
   J.codec = codec;
   J.n_slices = alg ? n_slices : 0;
@@ -443,7 +443,13 @@ int decompress_enqueue_a(Slot& S, const ChecksumTables& tabs, uint32_t alg, Deco
                     J.cks_got, st, launches);
     launch_checksum_compare(J.cks_got, J.slice_sum, J.slice_owner, J.slice_base, s, J.status, J.bad, st, launches);
   }
-  if (J.codec == B2S_CODEC_SNAPPY_XERIAL)
+  if (J.codec == B2S_CODEC_ZSTD) {
+    // no per-block descriptors: a frame is a serial unit; the size pass runs the sequence decoder without copying
+    rc = S.scratch.ensure(zstd_ws_bytes(n));
+    if (rc) return rc;
+    CU(cudaMemsetAsync(J.nblk, 0, (size_t)n * 8, st));
+    launch_zstd_sizes(d_src, J.src_off, J.src_len, n, (uint8_t*)S.scratch.p, J.olen, J.status, st, launches);
+  } else if (J.codec == B2S_CODEC_SNAPPY_XERIAL)
     launch_xerial_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.totals + 2, J.status, st, launches);
   else
     launch_lz4block_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.totals + 2, J.status, st, launches);
@@ -462,6 +468,18 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
                          uint64_t* launches) {
   J.nb = J.h_totals[0];
   J.total_out = J.h_totals[1];
+  if (J.codec == B2S_CODEC_ZSTD) {
+    cudaStream_t zst = S.st;
+    CU(cudaEventRecord(S.ev_t0, zst));
+    launch_zstd_decode(d_src, J.src_off, J.src_len, J.n, (uint8_t*)S.scratch.p, J.olen, d_dst, J.dst_off, dst_cap,
+                       J.status, zst, launches);
+    CU(cudaEventRecord(S.ev_t1, zst));
+    CU(cudaEventRecord(S.ev_k1, zst));
+    CU(cudaMemcpyAsync(J.h_down, J.d_down, J.down_bytes, cudaMemcpyDeviceToHost, zst));
+    CU(cudaEventRecord(S.ev_b, zst));
+    CU(cudaGetLastError());
+    return 0;
+  }
   if (J.nb >= 0xffffffffull) return fail(B2S_E_ARG, "too many codec blocks in one chunk%s");
   int rc = S.desc.ensure((size_t)(J.nb + 1) * sizeof(BlockDesc));
   if (rc) return rc;

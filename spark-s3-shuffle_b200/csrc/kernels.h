@@ -107,6 +107,16 @@ void launch_snappy_tokens(const BlockDesc* d_desc, uint32_t b0, uint32_t m, cons
                           uint32_t rec_stride, uint32_t* d_nrec, int32_t* d_status, cudaStream_t st,
                           uint64_t* launches);
 
+// ---------------- zstd.cu (K6: Zstandard frame decoding, thread per stream; core in zstd_core.h) ----------------
+size_t zstd_ws_bytes(uint32_t n_streams);
+// decoded size of every stream (status CORRUPT / UNSUPPORTED on malformed input; streams with status != 0 are skipped)
+void launch_zstd_sizes(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
+                       uint8_t* d_ws, uint64_t* d_olen, int32_t* d_status, cudaStream_t st, uint64_t* launches);
+// decodes stream i to dst_base + d_dst_off[i] (d_olen[i] bytes, as computed by launch_zstd_sizes)
+void launch_zstd_decode(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
+                        uint8_t* d_ws, uint64_t* d_olen, uint8_t* dst_base, const uint64_t* d_dst_off, uint64_t dst_cap,
+                        int32_t* d_status, cudaStream_t st, uint64_t* launches);
+
 // ---------------- gen.cu (bench utility) ----------------
 void launch_gen_terasort(uint8_t* d_dst, uint64_t first_record, uint64_t n_records, uint64_t seed, cudaStream_t st);
 

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match_kernel(
       __stcs(oq, (uint16_t)off);  // position < stride always (stride = block_size rounded up to 32)
       // Snappy (near_limit = 2048, blocks <= 32 KiB so L < 2^15): bit 15 tells the parse kernel that the offset fits
       // the 2-byte copy element, sparing it a dependent load of off[]
-      __stcs(mq, (uint16_t)(L | (off - 1u < near_limit - 1u ? 0x8000 : 0)));
+      __stcs(mq, (uint16_t)(L | ((off != 0u && off < near_limit) ? 0x8000 : 0)));
       oq += 32;
       mq += 32;
     };
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
   uint32_t ns = 0;
   bool fail = false;
   const int mflimit = n - kMFLimit;
-  if (mflimit >= 0) {
+  if (n >= kMFLimit + 1) {  // shorter blocks hold no match; the match kernel skipped them (nothing was written to ml[])
     const int groups = (mflimit >> 2) + 1;
     unsigned long long nxt = __ldcs(mlw);
     for (int g = 0; g < groups; g++) {

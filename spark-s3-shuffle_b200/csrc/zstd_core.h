@@ -1,0 +1,630 @@
+// zstd_core.h — Zstandard (RFC 8878) frame decoding, written once for host and device.
+//
+// Replaces, for spark.io.compression.codec=zstd, com.github.luben.zstd.ZstdInputStreamNoFinalizer [U] (zstd-jni 1.5.5-x ->
+// libzstd ZSTD_decompressStream) under serializerManager.wrapStream at storage/S3ShuffleReader.scala:107-109.
+// The same functions are compiled by nvcc into the kernels of zstd.cu (the product) and by the host compiler into the
+// unit test tests/test_zstd_core.py, which checks them against libzstd.so.1 on frames produced by libzstd itself
+// (levels 1..3, streaming mode without content size as zstd-jni writes them, raw/RLE/compressed blocks, Huffman
+// 1- and 4-stream literals, treeless literals, predefined/RLE/FSE/repeat sequence tables, repeat offsets,
+// concatenated and skippable frames).  Nothing here is a CPU fallback: the C ABI only ever launches the device build.
+//
+// Scope: frames without dictionary; window <= the decoded size the caller provides room for; Content_Checksum is
+// skipped, not verified (Spark's ZStdCompressionCodec leaves it off).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2S_HD __host__ __device__
+#else
+#define B2S_HD
+#endif
+
+namespace b2s {
+namespace zstd {
+
+constexpr int kErrCorrupt = -1;      // -> B2S_E_CORRUPT
+constexpr int kErrDstTooSmall = -3;  // -> B2S_E_DST_TOO_SMALL
+constexpr int kErrUnsupported = -4;  // -> B2S_E_UNSUPPORTED (dictionary)
+constexpr uint32_t kBlockMax = 128 * 1024;
+
+struct FseEntry {
+  uint8_t sym, nbits;
+  uint16_t base;
+};
+
+// per-frame decoder state; lives in global memory on the device (one per frame in flight)
+struct Workspace {
+  FseEntry ll[512], of[256], ml[512];
+  FseEntry wt[64];        // Huffman weights (FSE, accuracy <= 6)
+  uint16_t huf[2048];     // Huffman decoding table: symbol | nbits << 8, 2^maxbits entries (maxbits <= 11)
+  uint8_t weights[256];
+  uint8_t lit[kBlockMax + 64];
+  int16_t norm[64];
+  uint16_t next[64];
+  int ll_log, of_log, ml_log, huf_bits;
+  bool ll_ok, of_ok, ml_ok, huf_ok;
+  uint32_t rep[3];
+};
+
+B2S_HD inline int highbit32(uint32_t v) {  // position of the highest set bit, v != 0
+  int r = 0;
+  while (v >>= 1) r++;
+  return r;
+}
+
+// ---- LSB-first forward bit reader (FSE table descriptions) --------------------------------------------------
+struct BitsFwd {
+  const uint8_t* p;
+  uint64_t n;
+  uint64_t pos;  // bit position
+  B2S_HD uint32_t peek(int nb) const {
+    uint64_t v = 0;
+    const uint64_t b = pos >> 3;
+    for (int i = 0; i < 5; i++)
+      if (b + i < n) v |= (uint64_t)p[b + i] << (8 * i);
+    return (uint32_t)((v >> (pos & 7)) & ((1ull << nb) - 1));
+  }
+};
+
+// ---- backward bit reader (Huffman streams, sequence bitstream): starts below the final 1-bit marker ----------
+struct BitsRev {
+  const uint8_t* p;
+  int64_t n;
+  int64_t pos;  // bits still unread; may go negative (over-read: zeros), checked by the callers
+  B2S_HD bool init(const uint8_t* src, uint64_t len) {
+    p = src;
+    n = (int64_t)len;
+    if (len == 0 || src[len - 1] == 0) return false;
+    pos = (int64_t)(len - 1) * 8 + highbit32(src[len - 1]);
+    return true;
+  }
+  B2S_HD uint32_t read(int nb) {  // nb <= 32
+    if (nb == 0) return 0;
+    pos -= nb;
+    int64_t bp = pos;
+    int shift = 0;
+    int take = nb;
+    if (bp < 0) {  // bits below the start of the stream read as zero
+      shift = (int)(-bp);
+      if (shift >= nb) return 0;
+      take = nb - shift;
+      bp = 0;
+    }
+    uint64_t v = 0;
+    const int64_t b = bp >> 3;
+    for (int i = 0; i < 6; i++)
+      if (b + i < n) v |= (uint64_t)p[b + i] << (8 * i);
+    const uint32_t r = (uint32_t)((v >> (bp & 7)) & ((1ull << take) - 1));
+    return r << shift;
+  }
+};
+
+// ---- FSE -------------------------------------------------------------------------------------------------------
+// normalized counts -> decoding table (RFC 8878 4.1.1)
+B2S_HD inline bool fse_build(FseEntry* t, const int16_t* norm, int nsym, int log, uint16_t* next) {
+  const int size = 1 << log;
+  int high = size - 1;
+  for (int s = 0; s < nsym; s++) {
+    if (norm[s] == -1) {
+      t[high--].sym = (uint8_t)s;
+      next[s] = 1;
+    } else {
+      next[s] = (uint16_t)norm[s];
+    }
+  }
+  const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+  int pos = 0;
+  for (int s = 0; s < nsym; s++) {
+    for (int i = 0; i < norm[s]; i++) {
+      t[pos].sym = (uint8_t)s;
+      do pos = (pos + step) & mask;
+      while (pos > high);
+    }
+  }
+  if (pos != 0) return false;
+  for (int i = 0; i < size; i++) {
+    const int s = t[i].sym;
+    const uint32_t x = next[s]++;
+    const int nb = log - highbit32(x);
+    t[i].nbits = (uint8_t)nb;
+    t[i].base = (uint16_t)((x << nb) - size);
+  }
+  return true;
+}
+
+// reads a table description; returns bytes consumed (0 = malformed)
+B2S_HD inline uint64_t fse_read_header(const uint8_t* src, uint64_t n, int16_t* norm, int max_sym, int max_log, int* log_out,
+                                       int* nsym_out) {
+  BitsFwd b{src, n, 0};
+  if (n == 0) return 0;
+  const int log = (int)b.peek(4) + 5;
+  b.pos += 4;
+  if (log > max_log) return 0;
+  int remaining = 1 << log;
+  int sym = 0;
+  while (remaining > 0 && sym <= max_sym) {
+    const int bits = highbit32((uint32_t)(remaining + 1)) + 1;
+    uint32_t val = b.peek(bits);
+    const uint32_t lower = (1u << (bits - 1)) - 1;
+    const uint32_t threshold = (1u << bits) - 1 - (uint32_t)(remaining + 1);
+    if ((val & lower) < threshold) {
+      b.pos += bits - 1;
+      val &= lower;
+    } else if (val > lower) {
+      b.pos += bits;
+      val -= threshold;
+    } else {
+      b.pos += bits;
+    }
+    const int prob = (int)val - 1;
+    remaining -= prob < 0 ? -prob : prob;
+    norm[sym++] = (int16_t)prob;
+    if (prob == 0) {
+      uint32_t rep = b.peek(2);
+      b.pos += 2;
+      for (;;) {
+        for (uint32_t i = 0; i < rep && sym <= max_sym; i++) norm[sym++] = 0;
+        if (rep != 3) break;
+        rep = b.peek(2);
+        b.pos += 2;
+      }
+    }
+    if ((b.pos >> 3) > n) return 0;
+  }
+  if (remaining != 0 || sym > max_sym + 1) return 0;
+  *log_out = log;
+  *nsym_out = sym;
+  const uint64_t used = (b.pos + 7) >> 3;
+  return used <= n ? used : 0;
+}
+
+// ---- Huffman ---------------------------------------------------------------------------------------------------
+// weights[0..nw) given (the last one is implied) -> decoding table; returns false when malformed
+B2S_HD inline bool huf_build(Workspace* w, int nw) {
+  uint32_t sum = 0;
+  for (int i = 0; i < nw; i++) {
+    if (w->weights[i] > 11) return false;
+    if (w->weights[i]) sum += 1u << (w->weights[i] - 1);
+  }
+  if (sum == 0) return false;
+  const int maxbits = highbit32(sum) + 1;
+  if (maxbits > 11) return false;
+  const uint32_t left = (1u << maxbits) - sum;
+  if (left & (left - 1)) return false;  // the implied weight must complete a power of two
+  w->weights[nw] = (uint8_t)(highbit32(left) + 1);
+  const int nsym = nw + 1;
+  // number of codes per length, first table index per length (longest codes first)
+  uint32_t rank_count[13] = {0}, rank_idx[13];
+  for (int i = 0; i < nsym; i++) {
+    const int wt = w->weights[i];
+    rank_count[wt ? maxbits + 1 - wt : 0]++;
+  }
+  rank_idx[maxbits] = 0;
+  for (int i = maxbits; i >= 1; i--) rank_idx[i - 1] = rank_idx[i] + rank_count[i] * (1u << (maxbits - i));
+  if (rank_idx[0] != (1u << maxbits)) return false;
+  for (int i = 0; i < nsym; i++) {
+    const int wt = w->weights[i];
+    if (!wt) continue;
+    const int bits = maxbits + 1 - wt;
+    const uint32_t code = rank_idx[bits], len = 1u << (maxbits - bits);
+    for (uint32_t k = 0; k < len; k++) w->huf[code + k] = (uint16_t)(i | (bits << 8));
+    rank_idx[bits] += len;
+  }
+  w->huf_bits = maxbits;
+  return true;
+}
+
+// Huffman tree description; returns bytes consumed (0 = malformed)
+B2S_HD inline uint64_t huf_read_tree(Workspace* w, const uint8_t* src, uint64_t n) {
+  if (n == 0) return 0;
+  const int hb = src[0];
+  int nw = 0;
+  uint64_t used;
+  if (hb >= 128) {  // direct: 4 bits per weight
+    nw = hb - 127;
+    const uint64_t bytes = (uint64_t)(nw + 1) / 2;
+    if (1 + bytes > n) return 0;
+    for (int i = 0; i < nw; i++) {
+      const uint8_t v = src[1 + i / 2];
+      w->weights[i] = (i & 1) ? (v & 15) : (v >> 4);
+    }
+    used = 1 + bytes;
+  } else {  // FSE-compressed weights, two interleaved states
+    const uint64_t clen = (uint64_t)hb;
+    if (clen == 0 || 1 + clen > n) return 0;
+    int log = 0, nsym = 0;
+    const uint64_t h = fse_read_header(src + 1, clen, w->norm, 12, 6, &log, &nsym);  // weights 0..12 (only <= 11 are legal)
+    if (!h || h >= clen) return 0;
+    for (int i = nsym; i < 13; i++) w->norm[i] = 0;
+    if (!fse_build(w->wt, w->norm, nsym, log, w->next)) return 0;
+    BitsRev br;
+    if (!br.init(src + 1 + h, clen - h)) return 0;
+    uint32_t s1 = br.read(log), s2 = br.read(log);
+    for (;;) {
+      if (nw >= 254) return 0;
+      w->weights[nw++] = w->wt[s1].sym;
+      if (br.pos < w->wt[s1].nbits) {  // not enough bits for another update: flush the other state and stop
+        if (br.pos < 0) return 0;
+        w->weights[nw++] = w->wt[s2].sym;
+        break;
+      }
+      s1 = w->wt[s1].base + br.read(w->wt[s1].nbits);
+      if (nw >= 254) return 0;
+      w->weights[nw++] = w->wt[s2].sym;
+      if (br.pos < w->wt[s2].nbits) {
+        if (br.pos < 0) return 0;
+        w->weights[nw++] = w->wt[s1].sym;
+        break;
+      }
+      s2 = w->wt[s2].base + br.read(w->wt[s2].nbits);
+    }
+    used = 1 + clen;
+  }
+  if (nw < 1 || nw > 255) return 0;
+  if (!huf_build(w, nw)) return 0;
+  return used;
+}
+
+B2S_HD inline bool huf_decode_stream(const Workspace* w, const uint8_t* src, uint64_t n, uint8_t* out, uint64_t count) {
+  BitsRev br;
+  if (!br.init(src, n)) return false;
+  const int mb = w->huf_bits;
+  const uint32_t mask = (1u << mb) - 1;
+  uint32_t state = br.read(mb);
+  for (uint64_t i = 0; i < count; i++) {
+    const uint16_t e = w->huf[state];
+    out[i] = (uint8_t)e;
+    const int nb = e >> 8;
+    state = ((state << nb) & mask) | br.read(nb);
+  }
+  // every stream must be consumed exactly: the over-read equals the initial state's width
+  return br.pos == -(int64_t)mb;
+}
+
+// ---- sequences ---------------------------------------------------------------------------------------------------
+B2S_HD inline void ll_code(int c, uint32_t* base, int* bits) {
+  const uint32_t b[36] = {0,  1,  2,  3,  4,  5,  6,  7,  8,   9,   10,  11,   12,   13,   14,   15,    16,    18,
+                          20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
+  const uint8_t e[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+  *base = b[c];
+  *bits = e[c];
+}
+B2S_HD inline void ml_code(int c, uint32_t* base, int* bits) {
+  const uint32_t b[53] = {3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20,
+                          21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41,
+                          43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
+  const uint8_t e[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                         0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+  *base = b[c];
+  *bits = e[c];
+}
+
+// kind: 0 = literal lengths, 1 = offsets, 2 = match lengths
+B2S_HD inline bool seq_default_table(Workspace* w, int kind) {
+  const int16_t LL[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
+  const int16_t OF[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
+  const int16_t ML[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                          1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
+  if (kind == 0) {
+    for (int i = 0; i < 36; i++) w->norm[i] = LL[i];
+    w->ll_log = 6;
+    return fse_build(w->ll, w->norm, 36, 6, w->next);
+  }
+  if (kind == 1) {
+    for (int i = 0; i < 29; i++) w->norm[i] = OF[i];
+    w->of_log = 5;
+    return fse_build(w->of, w->norm, 29, 5, w->next);
+  }
+  for (int i = 0; i < 53; i++) w->norm[i] = ML[i];
+  w->ml_log = 6;
+  return fse_build(w->ml, w->norm, 53, 6, w->next);
+}
+
+// sets up one of the three sequence tables per its compression mode; returns bytes consumed or -1
+B2S_HD inline int64_t seq_setup_table(Workspace* w, int kind, int mode, const uint8_t* src, uint64_t n) {
+  FseEntry* t = kind == 0 ? w->ll : kind == 1 ? w->of : w->ml;
+  int* log = kind == 0 ? &w->ll_log : kind == 1 ? &w->of_log : &w->ml_log;
+  bool* ok = kind == 0 ? &w->ll_ok : kind == 1 ? &w->of_ok : &w->ml_ok;
+  const int max_sym = kind == 0 ? 35 : kind == 1 ? 31 : 52;
+  const int max_log = kind == 0 ? 9 : kind == 1 ? 8 : 9;
+  if (mode == 0) {
+    if (!seq_default_table(w, kind)) return -1;
+    *ok = true;
+    return 0;
+  }
+  if (mode == 1) {  // RLE: a single symbol, zero state bits
+    if (n < 1 || src[0] > max_sym) return -1;
+    t[0].sym = src[0];
+    t[0].nbits = 0;
+    t[0].base = 0;
+    *log = 0;
+    *ok = true;
+    return 1;
+  }
+  if (mode == 2) {
+    int l = 0, nsym = 0;
+    const uint64_t h = fse_read_header(src, n, w->norm, max_sym, max_log, &l, &nsym);
+    if (!h) return -1;
+    if (!fse_build(t, w->norm, nsym, l, w->next)) return -1;
+    *log = l;
+    *ok = true;
+    return (int64_t)h;
+  }
+  return *ok ? 0 : -1;  // repeat: the previous block's table must exist
+}
+
+// ---- blocks --------------------------------------------------------------------------------------------------------
+// Decodes one compressed block of `n` bytes.  out = start of the frame's output, op = bytes of the frame produced so
+// far (matches may reach back to out[0]); cap = room in out.  size_only: only count the regenerated size.
+// Returns the number of bytes the block regenerates, or a negative error.
+B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, uint64_t n, uint8_t* out, uint64_t op,
+                                              uint64_t cap, bool size_only) {
+  if (n < 1) return kErrCorrupt;
+  // ---- literals section
+  const int ltype = src[0] & 3, sf = (src[0] >> 2) & 3;
+  uint64_t hdr, regen, csize = 0;
+  int streams = 1;
+  if (ltype < 2) {
+    if (sf == 0 || sf == 2) {
+      hdr = 1;
+      regen = src[0] >> 3;
+    } else if (sf == 1) {
+      if (n < 2) return kErrCorrupt;
+      hdr = 2;
+      regen = (src[0] >> 4) | ((uint64_t)src[1] << 4);
+    } else {
+      if (n < 3) return kErrCorrupt;
+      hdr = 3;
+      regen = (src[0] >> 4) | ((uint64_t)src[1] << 4) | ((uint64_t)src[2] << 12);
+    }
+  } else {
+    if (sf < 2) {
+      if (n < 3) return kErrCorrupt;
+      hdr = 3;
+      const uint32_t v = src[0] | (src[1] << 8) | ((uint32_t)src[2] << 16);
+      regen = (v >> 4) & 0x3ff;
+      csize = (v >> 14) & 0x3ff;
+      streams = sf == 0 ? 1 : 4;
+    } else if (sf == 2) {
+      if (n < 4) return kErrCorrupt;
+      hdr = 4;
+      const uint32_t v = src[0] | (src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+      regen = (v >> 4) & 0x3fff;
+      csize = v >> 18;
+      streams = 4;
+    } else {
+      if (n < 5) return kErrCorrupt;
+      hdr = 5;
+      const uint64_t v = src[0] | (src[1] << 8) | ((uint64_t)src[2] << 16) | ((uint64_t)src[3] << 24) | ((uint64_t)src[4] << 32);
+      regen = (v >> 4) & 0x3ffff;
+      csize = v >> 22;
+      streams = 4;
+    }
+  }
+  if (regen > kBlockMax) return kErrCorrupt;
+  const uint8_t* lit = nullptr;  // literal bytes of this block (either inside src or in w->lit)
+  uint64_t ip = hdr;
+  if (ltype == 0) {
+    if (ip + regen > n) return kErrCorrupt;
+    lit = src + ip;
+    ip += regen;
+  } else if (ltype == 1) {
+    if (ip + 1 > n) return kErrCorrupt;
+    if (!size_only)
+      for (uint64_t i = 0; i < regen; i++) w->lit[i] = src[ip];
+    lit = w->lit;
+    ip += 1;
+  } else {
+    if (ip + csize > n) return kErrCorrupt;
+    const uint8_t* ls = src + ip;
+    uint64_t ln = csize;
+    if (ltype == 2) {
+      const uint64_t t = huf_read_tree(w, ls, ln);
+      if (!t) return kErrCorrupt;
+      w->huf_ok = true;
+      ls += t;
+      ln -= t;
+    } else if (!w->huf_ok) {
+      return kErrCorrupt;  // treeless without a previous table
+    }
+    if (!size_only) {
+      if (streams == 1) {
+        if (!huf_decode_stream(w, ls, ln, w->lit, regen)) return kErrCorrupt;
+      } else {
+        if (ln < 6) return kErrCorrupt;
+        const uint64_t s1 = ls[0] | (ls[1] << 8), s2 = ls[2] | (ls[3] << 8), s3 = ls[4] | (ls[5] << 8);
+        if (6 + s1 + s2 + s3 > ln) return kErrCorrupt;
+        const uint64_t s4 = ln - 6 - s1 - s2 - s3;
+        const uint64_t q = (regen + 3) / 4;
+        if (3 * q > regen) return kErrCorrupt;
+        const uint8_t* a = ls + 6;
+        if (!huf_decode_stream(w, a, s1, w->lit, q)) return kErrCorrupt;
+        if (!huf_decode_stream(w, a + s1, s2, w->lit + q, q)) return kErrCorrupt;
+        if (!huf_decode_stream(w, a + s1 + s2, s3, w->lit + 2 * q, q)) return kErrCorrupt;
+        if (!huf_decode_stream(w, a + s1 + s2 + s3, s4, w->lit + 3 * q, regen - 3 * q)) return kErrCorrupt;
+      }
+    }
+    lit = w->lit;
+    ip += csize;
+  }
+  // ---- sequences section
+  if (ip >= n) return kErrCorrupt;
+  uint32_t nseq = src[ip++];
+  if (nseq >= 128) {
+    if (nseq == 255) {
+      if (ip + 2 > n) return kErrCorrupt;
+      nseq = src[ip] + (src[ip + 1] << 8) + 0x7F00;
+      ip += 2;
+    } else {
+      if (ip + 1 > n) return kErrCorrupt;
+      nseq = ((nseq - 128) << 8) + src[ip];
+      ip += 1;
+    }
+  }
+  uint64_t produced = 0;
+  uint64_t lpos = 0;
+  if (nseq) {
+    if (ip >= n) return kErrCorrupt;
+    const int modes = src[ip++];
+    if (modes & 3) return kErrCorrupt;
+    for (int kind = 0; kind < 3; kind++) {
+      const int mode = (modes >> (6 - 2 * kind)) & 3;
+      const int64_t used = seq_setup_table(w, kind, mode, src + ip, n - ip);
+      if (used < 0) return kErrCorrupt;
+      ip += (uint64_t)used;
+    }
+    BitsRev br;
+    if (ip >= n || !br.init(src + ip, n - ip)) return kErrCorrupt;
+    uint32_t sl = br.read(w->ll_log), so = br.read(w->of_log), sm = br.read(w->ml_log);
+    for (uint32_t i = 0; i < nseq; i++) {
+      const int oc = w->of[so].sym, mc = w->ml[sm].sym, lc = w->ll[sl].sym;
+      if (oc > 31 || mc > 52 || lc > 35) return kErrCorrupt;
+      uint32_t mlb, llb;
+      int mle, lle;
+      ml_code(mc, &mlb, &mle);
+      ll_code(lc, &llb, &lle);
+      // extra bits: offset, match length, literal length — in that order
+      const uint32_t ofv = (oc ? (1u << oc) : 1u) + br.read(oc);
+      const uint32_t mlen = mlb + br.read(mle);
+      const uint32_t llen = llb + br.read(lle);
+      // offset: values 1..3 are repeat codes
+      uint32_t offset;
+      if (ofv > 3) {
+        offset = ofv - 3;
+        w->rep[2] = w->rep[1];
+        w->rep[1] = w->rep[0];
+        w->rep[0] = offset;
+      } else {
+        uint32_t idx = ofv - 1;
+        if (llen == 0) idx++;
+        if (idx == 0) {
+          offset = w->rep[0];
+        } else {
+          offset = idx < 3 ? w->rep[idx] : w->rep[0] - 1;
+          if (idx > 1) w->rep[2] = w->rep[1];
+          w->rep[1] = w->rep[0];
+          w->rep[0] = offset;
+        }
+      }
+      if (offset == 0) return kErrCorrupt;
+      if (lpos + llen > regen) return kErrCorrupt;
+      if (produced + llen + mlen > kBlockMax) return kErrCorrupt;
+      if (!size_only) {
+        const uint64_t o = op + produced;
+        if (o + llen + mlen > cap) return kErrDstTooSmall;
+        if ((uint64_t)offset > o + llen) return kErrCorrupt;  // reaches before the start of the frame
+        for (uint32_t k = 0; k < llen; k++) out[o + k] = lit[lpos + k];
+        uint8_t* d = out + o + llen;
+        const uint8_t* s = d - offset;
+        for (uint32_t k = 0; k < mlen; k++) d[k] = s[k];
+      }
+      lpos += llen;
+      produced += (uint64_t)llen + mlen;
+      if (i + 1 < nseq) {  // state updates: literal length, match length, offset
+        sl = w->ll[sl].base + br.read(w->ll[sl].nbits);
+        sm = w->ml[sm].base + br.read(w->ml[sm].nbits);
+        so = w->of[so].base + br.read(w->of[so].nbits);
+      }
+    }
+    if (br.pos != 0) return kErrCorrupt;  // the bitstream must be consumed exactly
+  }
+  // remaining literals
+  const uint64_t tail = regen - lpos;
+  if (produced + tail > kBlockMax) return kErrCorrupt;
+  if (!size_only) {
+    const uint64_t o = op + produced;
+    if (o + tail > cap) return kErrDstTooSmall;
+    for (uint64_t k = 0; k < tail; k++) out[o + k] = lit[lpos + k];
+  }
+  return (int64_t)(produced + tail);
+}
+
+// Decodes every frame in src[0..n) (concatenated frames, skippable frames) into dst; returns the decoded size or a
+// negative error.  size_only: dst/cap are ignored.
+B2S_HD inline int64_t decode_stream(Workspace* w, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, bool size_only) {
+  uint64_t ip = 0, total = 0;
+  while (ip < n) {
+    if (n - ip < 4) return kErrCorrupt;
+    const uint32_t magic = src[ip] | (src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16) | ((uint32_t)src[ip + 3] << 24);
+    ip += 4;
+    if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
+      if (n - ip < 4) return kErrCorrupt;
+      const uint64_t sz = src[ip] | (src[ip + 1] << 8) | ((uint64_t)src[ip + 2] << 16) | ((uint64_t)src[ip + 3] << 24);
+      ip += 4;
+      if (sz > n - ip) return kErrCorrupt;
+      ip += sz;
+      continue;
+    }
+    if (magic != 0xFD2FB528u) return kErrCorrupt;
+    if (ip >= n) return kErrCorrupt;
+    const int fhd = src[ip++];
+    const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, checksum = (fhd >> 2) & 1, did_flag = fhd & 3;
+    if (fhd & 0x08) return kErrCorrupt;  // reserved bit
+    if (!single) {
+      if (ip >= n) return kErrCorrupt;
+      ip++;  // window descriptor: the whole frame output is addressable here, so the size itself is not needed
+    }
+    const int did_bytes = did_flag == 0 ? 0 : did_flag == 1 ? 1 : did_flag == 2 ? 2 : 4;
+    if (ip + did_bytes > n) return kErrCorrupt;
+    uint32_t did = 0;
+    for (int i = 0; i < did_bytes; i++) did |= (uint32_t)src[ip + i] << (8 * i);
+    ip += did_bytes;
+    if (did != 0) return kErrUnsupported;
+    const int fcs_bytes = fcs_flag == 0 ? (single ? 1 : 0) : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+    if (ip + fcs_bytes > n) return kErrCorrupt;
+    uint64_t fcs = 0;
+    for (int i = 0; i < fcs_bytes; i++) fcs |= (uint64_t)src[ip + i] << (8 * i);
+    if (fcs_bytes == 2) fcs += 256;
+    ip += fcs_bytes;
+    // frame state
+    w->rep[0] = 1;
+    w->rep[1] = 4;
+    w->rep[2] = 8;
+    w->ll_ok = w->of_ok = w->ml_ok = w->huf_ok = false;
+    uint8_t* out = size_only ? nullptr : dst + total;
+    const uint64_t room = size_only ? 0 : cap - total;
+    uint64_t op = 0;
+    for (;;) {
+      if (ip + 3 > n) return kErrCorrupt;
+      const uint32_t bh = src[ip] | (src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16);
+      ip += 3;
+      const int last = bh & 1, type = (bh >> 1) & 3;
+      const uint32_t bsize = bh >> 3;
+      if (type == 3 || bsize > kBlockMax) return kErrCorrupt;
+      if (type == 0) {
+        if (bsize > n - ip) return kErrCorrupt;
+        if (!size_only) {
+          if (op + bsize > room) return kErrDstTooSmall;
+          for (uint32_t k = 0; k < bsize; k++) out[op + k] = src[ip + k];
+        }
+        ip += bsize;
+        op += bsize;
+      } else if (type == 1) {
+        if (ip >= n) return kErrCorrupt;
+        if (!size_only) {
+          if (op + bsize > room) return kErrDstTooSmall;
+          for (uint32_t k = 0; k < bsize; k++) out[op + k] = src[ip];
+        }
+        ip += 1;
+        op += bsize;
+      } else {
+        if (bsize > n - ip) return kErrCorrupt;
+        const int64_t r = decode_compressed_block(w, src + ip, bsize, out, op, room, size_only);
+        if (r < 0) return r;
+        ip += bsize;
+        op += (uint64_t)r;
+      }
+      if (last) break;
+    }
+    if (fcs_bytes && fcs != op) return kErrCorrupt;
+    if (checksum) {
+      if (ip + 4 > n) return kErrCorrupt;
+      ip += 4;
+    }
+    total += op;
+  }
+  return (int64_t)total;
+}
+
+}  // namespace zstd
+}  // namespace b2s

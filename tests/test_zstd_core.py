@@ -1,0 +1,94 @@
+"""The Zstandard decoder core (spark-s3-shuffle_b200/csrc/zstd_core.h — the functions the CUDA kernels call) compiled
+for the host and pinned on libzstd.so.1: frames produced by the real library, in the shapes zstd-jni writes them."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import zstd_ref
+from conftest import KINDS, corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def zc(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("zc") / "libzc.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out,
+                           os.path.join(ROOT, "tests", "native", "zstd_core_host.cpp")])
+    L = C.CDLL(out)
+    L.zc_decode.restype = C.c_longlong
+    L.zc_decode.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong]
+    L.zc_size.restype = C.c_longlong
+    L.zc_size.argtypes = [C.c_char_p, C.c_ulonglong]
+    return L
+
+
+def decode(zc, frame, cap):
+    out = C.create_string_buffer(max(cap, 1))
+    r = zc.zc_decode(frame, len(frame), out, cap)
+    return r, out.raw[:max(r, 0)]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_one_shot_frames_levels_1_to_3(zc, oracle, kind):
+    for n in (0, 1, 10, 100, 1000, 5000, 40000, 131072, 131073, 400000):
+        d = corpus(oracle, kind, n, seed=2)
+        for lvl in (1, 2, 3):
+            f = zstd_ref.compress(d, lvl)
+            r, out = decode(zc, f, n)
+            assert r == n and out == d, (kind, n, lvl, r)
+            assert zc.zc_size(f, len(f)) == n
+
+
+@pytest.mark.parametrize("kind", ["terasort", "text", "runs", "ints", "random"])
+def test_streaming_frames_as_zstd_jni_writes_them(zc, oracle, kind):
+    """no Frame_Content_Size, window descriptor, 32 KiB writes, optional flushes (block boundaries mid-frame)"""
+    for n in (0, 5, 32768, 100000, 700000):
+        d = corpus(oracle, kind, n, seed=3)
+        for lvl, flush in ((1, 0), (3, 0), (1, 2), (3, 5)):
+            f = zstd_ref.compress_stream(d, lvl, 32768, flush)
+            assert zstd_ref.decompress(f) == d
+            r, out = decode(zc, f, n)
+            assert r == n and out == d, (kind, n, lvl, flush, r)
+            assert zc.zc_size(f, len(f)) == n
+
+
+def test_concatenated_and_skippable_frames(zc, oracle):
+    a, b = corpus(oracle, "text", 70000, 1), corpus(oracle, "terasort", 50000, 2)
+    skip = (0x184D2A53).to_bytes(4, "little") + (5).to_bytes(4, "little") + b"hello"
+    f = zstd_ref.compress_stream(a, 1) + skip + zstd_ref.compress(b, 3) + zstd_ref.compress(b"", 1)
+    r, out = decode(zc, f, len(a) + len(b))
+    assert r == len(a) + len(b) and out == a + b
+    assert zstd_ref.decompress(f) == a + b
+
+
+def test_destination_too_small_and_truncation(zc, oracle):
+    d = corpus(oracle, "text", 50000, 4)
+    f = zstd_ref.compress_stream(d, 3)
+    assert decode(zc, f, len(d) - 1)[0] == -3
+    for cut in (1, 3, 5, 9, len(f) // 2, len(f) - 1):
+        assert decode(zc, f[:cut], len(d))[0] < 0
+
+
+def test_bit_flips_never_crash_and_agree_with_libzstd_when_it_rejects(zc, oracle):
+    rng = np.random.default_rng(5)
+    d = corpus(oracle, "terasort", 60000, 6)
+    f = bytearray(zstd_ref.compress_stream(d, 1))
+    accepted_wrong = 0
+    for _ in range(300):
+        g = bytearray(f)
+        i = int(rng.integers(0, len(g)))
+        g[i] ^= 1 << int(rng.integers(0, 8))
+        r, out = decode(zc, bytes(g), len(d) + 1024)
+        try:
+            ref = zstd_ref.decompress(bytes(g))
+        except IOError:
+            ref = None
+        if r >= 0 and ref is not None:
+            assert out == ref          # both accept: same bytes
+        elif r >= 0 and ref is None:
+            accepted_wrong += 1        # we accepted what libzstd rejects (no checksum in the frame: tolerated, counted)
+    assert accepted_wrong <= 30
