@@ -42,8 +42,9 @@ int fail_cuda(const char* what, cudaError_t e) {
     if (e__ != cudaSuccess) return fail_cuda(#call, e__);  \
   } while (0)
 
-constexpr int NSLOT = 3;
-constexpr uint64_t kChunkBytes = 64ull << 20;
+constexpr int NSLOT = 4;
+uint64_t g_host_chunk_bytes = 256ull << 20;  // host-pointer calls: bytes per pipeline chunk (B2S_HOST_CHUNK_MB).  The thread-per-block
+                                              // kernels cost ~2 ms per launch whatever the block count, so chunks must be large enough to amortise them
 constexpr uint32_t kChunkStreams = 1u << 18;
 constexpr uint32_t kXxhSeed = 0x9747b28cu;
 uint32_t g_lz4_chunk_blocks = 32768;  // codec blocks per match/parse/emit (or tokens/copy) pass: bounds the workspace; B2S_LZ4_CHUNK_BLOCKS
@@ -502,17 +503,29 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
     const uint32_t nb = (uint32_t)J.nb;
     const uint32_t rec_stride = lz4_decode_rec_stride(J.codec, (uint32_t)max_olen, (uint32_t)max_clen);
     const uint32_t chunk = std::min<uint32_t>(nb, g_lz4_chunk_blocks);
-    rc = S.scratch.ensure(lz4_decode_ws_bytes(chunk, rec_stride) + align_up((size_t)nb * 4, 256));
+    const size_t nrec_bytes = align_up((size_t)nb * 4, 256);
+    const size_t ws_bytes = align_up(lz4_decode_ws_bytes(chunk, rec_stride), 256);
+    rc = S.scratch.ensure(nrec_bytes + ws_bytes * (nb > chunk ? 2 : 1));
     if (rc) return rc;
     uint32_t* nrec = (uint32_t*)S.scratch.p;
-    uint8_t* ws = (uint8_t*)S.scratch.p + align_up((size_t)nb * 4, 256);
-    for (uint32_t b0 = 0; b0 < nb; b0 += chunk) {
+    // token walk (thread per block, latency bound) of chunk k+1 on the side stream, copies of chunk k on the main one
+    CU(cudaEventRecord(S.ev_fork, st));
+    CU(cudaStreamWaitEvent(S.st2, S.ev_fork, 0));
+    uint32_t k = 0;
+    for (uint32_t b0 = 0; b0 < nb; b0 += chunk, k++) {
+      const uint32_t m = std::min<uint32_t>(chunk, nb - b0);
+      const int par = (int)(k & 1);
+      uint8_t* ws = (uint8_t*)S.scratch.p + nrec_bytes + (size_t)par * ws_bytes;
+      if (k >= 2) CU(cudaStreamWaitEvent(S.st2, S.ev_free[par], 0));
+      launch_lz4_tokens(J.codec, desc, b0, m, rec_stride, d_src, ws, nrec, J.status, S.st2, launches);
+      CU(cudaEventRecord(S.ev_match[par], S.st2));
+      CU(cudaStreamWaitEvent(st, S.ev_match[par], 0));
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       S.dom_pair(&e0, &e1);
       CU(cudaEventRecord(e0, st));
-      launch_lz4_decode_chunk(J.codec, desc, b0, std::min<uint32_t>(chunk, nb - b0), rec_stride, d_src, d_dst, ws, nrec,
-                              J.status, st, launches);
+      launch_lz4_copy(desc, b0, m, rec_stride, d_src, d_dst, ws, nrec, st, launches);
       CU(cudaEventRecord(e1, st));
+      CU(cudaEventRecord(S.ev_free[par], st));
     }
   } else if (J.nb) {
     launch_lz4_decompress(desc, (uint32_t)J.nb, d_src, d_dst, J.status, J.counter, st, launches);
@@ -546,7 +559,7 @@ void add_timing(Slot& S, bool copies) {
   if (copies) t_timing.h2d_ms += ms_between(S.ev_h0, S.ev_h1);  // d2h is added once the payload copy has run
 }
 
-// groups streams [i0, i1) into chunks of ~kChunkBytes
+// groups streams [i0, i1) into chunks of ~g_host_chunk_bytes
 void make_chunks(uint32_t n, const uint64_t* len, std::vector<uint32_t>& starts) {
   starts.clear();
   uint32_t i = 0;
@@ -554,7 +567,7 @@ void make_chunks(uint32_t n, const uint64_t* len, std::vector<uint32_t>& starts)
     starts.push_back(i);
     uint64_t bytes = 0;
     uint32_t cnt = 0;
-    while (i < n && cnt < kChunkStreams && (cnt == 0 || bytes + len[i] <= kChunkBytes)) {
+    while (i < n && cnt < kChunkStreams && (cnt == 0 || bytes + len[i] <= g_host_chunk_bytes)) {
       bytes += len[i];
       i++;
       cnt++;
@@ -630,6 +643,7 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
   g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
   g_lz4_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4_CHUNK_BLOCKS", (int)g_lz4_chunk_blocks));
   g_lz4d_legacy = env_int("B2S_LZ4D_LEGACY", 0);
+  g_host_chunk_bytes = (uint64_t)std::max(1, env_int("B2S_HOST_CHUNK_MB", (int)(g_host_chunk_bytes >> 20))) << 20;
   Context* C = new Context();
   for (int d = 0; d < count && d < 32; d++) {
     if (gpu_mask && !(gpu_mask & (1u << d))) continue;
@@ -1256,10 +1270,12 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
     return 0;
   };
 
+  // software pipeline over the chunks: enqueue chunk c's upload + phase A first (never blocks on younger work), then
+  // phase B of chunk c-1 (waits for its sizes), then the download of chunk c-2 (waits for its decode)
   for (size_t c = 0; c < nchunks + 2; c++) {
-    if (c >= 2 && c - 2 < nchunks && (rc = stage_c(c - 2))) return rc;
     if (c < nchunks && (rc = stage_a(c))) return rc;
     if (c >= 1 && c - 1 < nchunks && (rc = stage_b(c - 1))) return rc;
+    if (c >= 2 && c - 2 < nchunks && (rc = stage_c(c - 2))) return rc;
   }
   for (int k = 0; k < NSLOT; k++) {
     CU(cudaStreamSynchronize(D->slot[k].st));

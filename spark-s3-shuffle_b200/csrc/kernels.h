@@ -82,11 +82,15 @@ void launch_lz4_decompress(const BlockDesc* d_desc, uint32_t n_blocks, const uin
 // ---------------- lz4_decode.cu (K4: tokens + copy; codec blocks <= 64 KiB; the copy kernel also serves Snappy) ------
 uint32_t lz4_decode_rec_stride(uint32_t codec, uint32_t max_olen, uint32_t max_clen);
 size_t lz4_decode_ws_bytes(uint32_t chunk_blocks, uint32_t rec_stride);
-// decodes codec blocks [b0, b0+m): per-sequence records into d_ws, then the byte copies; d_nrec is indexed by global
-// block id.  Malformed blocks set status[stream] = B2S_E_CORRUPT.
-void launch_lz4_decode_chunk(uint32_t codec, const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t rec_stride,
-                             const uint8_t* src_base, uint8_t* dst_base, uint8_t* d_ws, uint32_t* d_nrec,
-                             int32_t* d_status, cudaStream_t st, uint64_t* launches);
+// codec blocks [b0, b0+m): launch_lz4_tokens writes per-sequence records into d_ws (LZ4 or Snappy element grammar;
+// malformed blocks set status[stream] = B2S_E_CORRUPT), launch_lz4_copy performs the byte copies from them.  d_nrec is
+// indexed by global block id.  Two calls so that the token walk of chunk k+1 can run beside the copies of chunk k.
+void launch_lz4_tokens(uint32_t codec, const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t rec_stride,
+                       const uint8_t* src_base, uint8_t* d_ws, uint32_t* d_nrec, int32_t* d_status, cudaStream_t st,
+                       uint64_t* launches);
+void launch_lz4_copy(const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t rec_stride, const uint8_t* src_base,
+                     uint8_t* dst_base, const uint8_t* d_ws, const uint32_t* d_nrec, cudaStream_t st,
+                     uint64_t* launches);
 
 // ---------------- snappy.cu (K5: xerial framing, Snappy emit / tokens; match, parse and copy kernels are shared) ------
 void launch_snappy_emit(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,

@@ -288,22 +288,32 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
   bool fail = false;
   const int mflimit = n - kMFLimit;
   if (n >= kMFLimit + 1) {  // shorter blocks hold no match; the match kernel skipped them (nothing was written to ml[])
-    const int groups = (mflimit >> 2) + 1;
-    unsigned long long nxt = __ldcs(mlw);
+    // 8 positions (one 16-byte load, the next one already in flight) per trip; a match is >= 4 long, so at most two
+    // sequences start in a group: the body is two copies of the same straight-line "take" code, 32-bit arithmetic only
+    const uint4* __restrict__ mlv = reinterpret_cast<const uint4*>(mlw);
+    const int groups = (mflimit >> 3) + 1;
+    uint4 nxt = __ldcs(mlv);
     for (int g = 0; g < groups; g++) {
-      const unsigned long long cur = nxt;
-      nxt = __ldcs(mlw + (g + 1 < groups ? g + 1 : g));
+      const uint4 cur = nxt;
+      nxt = __ldcs(mlv + (g + 1 < groups ? g + 1 : g));
       // each lane streams through its own block, so a miss costs a full DRAM round trip (~2000 cycles) against
-      // ~150 cycles of work per group: pull the sector needed 8 sectors (32 groups) from now into L1 already
-      if ((g & 3) == 0 && g + 32 < groups) asm volatile("prefetch.global.L1 [%0];" ::"l"(mlw + g + 32));
-      const int rel = p - 4 * g;  // >= 0; >= 4 while a match taken earlier still covers this group
-      if (rel < 4) {
-        const unsigned long long w = cur >> (16 * rel);
-        if (w) {
-          const int bit = (__ffsll((long long)w) - 1) & ~15;
-          p += bit >> 4;
-          const int mlw16 = (int)((w >> bit) & 0xffffu);
+      // ~150 cycles of work per group: pull the sector needed 8 sectors (16 groups) from now into L1 already
+      if ((g & 1) == 0 && g + 16 < groups) asm volatile("prefetch.global.L1 [%0];" ::"l"(mlv + g + 16));
+      const int base = 8 * g;
+      if (p >= base + 8) continue;  // a match taken earlier covers the whole group (uniform-ish, cheap)
+      unsigned nz = (cur.x & 0xffffu ? 1u : 0u) | (cur.x >> 16 ? 2u : 0u) | (cur.y & 0xffffu ? 4u : 0u) |
+                    (cur.y >> 16 ? 8u : 0u) | (cur.z & 0xffffu ? 16u : 0u) | (cur.z >> 16 ? 32u : 0u) |
+                    (cur.w & 0xffffu ? 64u : 0u) | (cur.w >> 16 ? 128u : 0u);
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const int rel = p - base;  // >= 0
+        const unsigned m = rel < 8 ? (nz & (0xffu << rel)) : 0u;
+        if (m) {
+          const int idx = __ffs(m) - 1;
+          const uint32_t word = idx < 4 ? (idx < 2 ? cur.x : cur.y) : (idx < 6 ? cur.z : cur.w);
+          const int mlw16 = (int)((idx & 1) ? word >> 16 : word & 0xffffu);
           const int ml = SNAPPY ? (mlw16 & 0x7fff) : mlw16;
+          p = base + idx;
           const int lit = p - anchor;
           int size;
           if (SNAPPY) {
@@ -327,16 +337,17 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
           }
           if (op + size > cap) {
             fail = true;
-            break;
+          } else {
+            seq[ns++] = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)ml | ((uint32_t)op << 16));
+            op += size;
+            p += ml;
+            anchor = p;
           }
-          seq[ns++] = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)ml | ((uint32_t)op << 16));
-          op += size;
-          p += ml;
-          anchor = p;
-        } else {
-          p = 4 * g + 4;
+        } else if (rel < 8) {
+          p = base + 8;
         }
       }
+      if (fail) break;
     }
   }
   if (SNAPPY) {

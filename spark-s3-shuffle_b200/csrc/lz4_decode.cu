@@ -165,18 +165,36 @@ __global__ void __launch_bounds__(kCopyThreads) lz4_copy_kernel(const BlockDesc*
     }
     __syncwarp();
 
-    // ---- matches, in dependency rounds
+    // ---- matches, in dependency rounds.  Outputs of the batch are disjoint and ordered by lane, so the matches a
+    // lane depends on — those whose output intersects its source [msrc, min(msrc+ml, mdst)) (the part of the source
+    // that is its OWN output is produced by the sequential copy itself) — form a contiguous lane range [jlo, jhi],
+    // found by two 5-step binary searches over the lane-sorted interval ends / starts.  A lane copies as soon as
+    // every match in its range is done; the number of rounds is the depth of the dependency chain, not its length.
     const int mdst = op + lit;
     const int msrc = mdst - off;
+    const int mend = mdst + ml;                          // non-decreasing across lanes (ml == 0: empty interval)
+    const int send = msrc + ml < mdst ? msrc + ml : mdst;
+    const unsigned matchmask = __ballot_sync(FULL, ml > 0);
+    int jlo = 0, jhi1 = 0;  // first lane whose output ends above msrc ; number of lanes whose output starts below send
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const int e = __shfl_sync(FULL, mend, jlo + step - 1);
+      const int b = __shfl_sync(FULL, mdst, jhi1 + step - 1);
+      if (e <= msrc) jlo += step;
+      if (b < send) jhi1 += step;
+    }
+    // (32 lanes: the searches cover indices 0..30; lane 31 can only matter to itself)
+    unsigned need = 0;
+    if (ml > 0) {
+      const int hi = jhi1 < lane ? jhi1 : lane;  // exclusive upper bound, only lanes below me
+      if (jlo < hi) need = ((hi >= 32 ? FULL : (1u << hi) - 1u) & ~((1u << jlo) - 1u)) & matchmask;
+    }
+    unsigned done = ~matchmask;
     bool pending = ml > 0;
-    unsigned pendmask = __ballot_sync(FULL, pending);
-    while (pendmask) {
-      const int first = __ffs(pendmask) - 1;                 // earliest unfinished match
-      const int frontier = __shfl_sync(FULL, mdst, first);   // everything below its output is final
-      const bool ready = pending && (lane == first || msrc + ml <= frontier);
-      const unsigned readymask = __ballot_sync(FULL, ready);
+    while (done != FULL) {
+      const bool ready = pending && (need & ~done) == 0;
       if (ready && ml <= 16) {
-        // sequential byte copy: also right for an overlapping match (off < ml), which can only be `first`
+        // sequential byte copy: also right for an overlapping match (off < ml)
         for (int j = 0; j < ml; j++) out[mdst + j] = out[msrc + j];
       }
       unsigned longmask = __ballot_sync(FULL, ready && ml > 16);
@@ -186,15 +204,20 @@ __global__ void __launch_bounds__(kCopyThreads) lz4_copy_kernel(const BlockDesc*
         const int ml_l = __shfl_sync(FULL, ml, l), off_l = __shfl_sync(FULL, off, l);
         uint8_t* o = out + __shfl_sync(FULL, mdst, l);
         const uint8_t* sp = o - off_l;
-        if (off_l >= ml_l && ml_l >= 96) {
-          group_copy<32>(o, sp, (uint32_t)ml_l, lane);
+        if (off_l >= ml_l) {  // disjoint source: plain cooperative copy
+          if (ml_l >= 96) group_copy<32>(o, sp, (uint32_t)ml_l, lane);
+          else
+            for (int j = lane; j < ml_l; j += 32) o[j] = sp[j];
+        } else if (off_l == 1) {  // byte run (the commonest overlapping match)
+          const uint8_t v = sp[0];
+          for (int j = lane; j < ml_l; j += 32) o[j] = v;
         } else {
           // overlapping match (off < ml): every byte comes from the already complete window [o - off, o)
-          for (int j = lane; j < ml_l; j += 32) o[j] = sp[j >= off_l ? (int)((unsigned)j % (unsigned)off_l) : j];
+          for (int j = lane; j < ml_l; j += 32) o[j] = sp[(unsigned)j % (unsigned)off_l];
         }
       }
+      done |= __ballot_sync(FULL, ready);
       pending = pending && !ready;
-      pendmask &= ~readymask;
       __syncwarp();  // this round's bytes are visible to the next round's loads
     }
   }
@@ -211,18 +234,27 @@ size_t lz4_decode_ws_bytes(uint32_t chunk_blocks, uint32_t rec_stride) {
   return (size_t)chunk_blocks * rec_stride * 8 + 256;
 }
 
-void launch_lz4_decode_chunk(uint32_t codec, const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t rec_stride,
-                             const uint8_t* src_base, uint8_t* dst_base, uint8_t* d_ws, uint32_t* d_nrec,
-                             int32_t* d_status, cudaStream_t st, uint64_t* launches) {
+// tokens and copy are launched separately so the runtime can put the (latency-bound) token walk of chunk k+1 on a side
+// stream beside the (issue-bound) copies of chunk k
+void launch_lz4_tokens(uint32_t codec, const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t rec_stride,
+                       const uint8_t* src_base, uint8_t* d_ws, uint32_t* d_nrec, int32_t* d_status, cudaStream_t st,
+                       uint64_t* launches) {
   if (!m) return;
   uint2* rec = reinterpret_cast<uint2*>(d_ws);
-  if (codec == B2S_CODEC_SNAPPY_XERIAL)
+  if (codec == B2S_CODEC_SNAPPY_XERIAL) {
     launch_snappy_tokens(d_desc, b0, m, src_base, rec, rec_stride, d_nrec, d_status, st, launches);
-  else
+  } else {
     lz4_tokens_kernel<<<(m + 63) / 64, 64, 0, st>>>(d_desc, b0, m, src_base, rec, rec_stride, d_nrec, d_status);
+    *launches += 1;
+  }
+}
+void launch_lz4_copy(const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t rec_stride, const uint8_t* src_base,
+                     uint8_t* dst_base, const uint8_t* d_ws, const uint32_t* d_nrec, cudaStream_t st,
+                     uint64_t* launches) {
+  if (!m) return;
   lz4_copy_kernel<<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
-      d_desc, b0, m, src_base, dst_base, rec, rec_stride, d_nrec);
-  *launches += 2;
+      d_desc, b0, m, src_base, dst_base, reinterpret_cast<const uint2*>(d_ws), rec_stride, d_nrec);
+  *launches += 1;
 }
 
 }  // namespace b2s
