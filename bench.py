@@ -32,7 +32,7 @@ N_BLOCKS_FULL = 16000               # 80 maps x 200 reduce partitions  => 10.000
 LZ4_BLOCK = 32768
 # dram__bytes_read.sum + dram__bytes_write.sum of one lz4_match_kernel launch over a 1.25 GiB chunk (ncu --set full,
 # profiles/r1c_*), scaled to the bench's 1 GiB chunks at run time; None until a capture of the current kernel exists
-NCU_TRAFFIC_PER_LAUNCH = None
+NCU_TRAFFIC_PER_LAUNCH = 6089710000  # 1.948 GB read + 4.141 GB written, full 32,768-block launch (profiles/r1p_multikernel_lz4.md)
 METRIC = "shuffle write+read GB/s (compress+CRC) at 1/2/4/8 B200 vs JVM-LZ4 CPU baseline"
 
 

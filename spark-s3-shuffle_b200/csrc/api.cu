@@ -48,6 +48,7 @@ uint64_t g_host_chunk_bytes = 256ull << 20;  // host-pointer calls: bytes per pi
 constexpr uint32_t kChunkStreams = 1u << 18;
 constexpr uint32_t kXxhSeed = 0x9747b28cu;
 uint32_t g_lz4_chunk_blocks = 32768;  // codec blocks per match/parse/emit (or tokens/copy) pass: bounds the workspace; B2S_LZ4_CHUNK_BLOCKS
+uint32_t g_lz4d_chunk_blocks = 65536;  // decode side: the token walk is latency bound, more blocks per launch = more loads in flight; B2S_LZ4D_CHUNK_BLOCKS
 int g_lz4d_legacy = 0;  // B2S_LZ4D_LEGACY=1: single-kernel tile decoder for every block size (A/B comparisons)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -502,7 +503,7 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
     // tokens (thread per block) + copy (lane per sequence), in chunks that bound the record workspace
     const uint32_t nb = (uint32_t)J.nb;
     const uint32_t rec_stride = lz4_decode_rec_stride(J.codec, (uint32_t)max_olen, (uint32_t)max_clen);
-    const uint32_t chunk = std::min<uint32_t>(nb, g_lz4_chunk_blocks);
+    const uint32_t chunk = std::min<uint32_t>(nb, g_lz4d_chunk_blocks);
     const size_t nrec_bytes = align_up((size_t)nb * 4, 256);
     const size_t ws_bytes = align_up(lz4_decode_ws_bytes(chunk, rec_stride), 256);
     rc = S.scratch.ensure(nrec_bytes + ws_bytes * (nb > chunk ? 2 : 1));
@@ -643,6 +644,7 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
   g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
   g_lz4_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4_CHUNK_BLOCKS", (int)g_lz4_chunk_blocks));
   g_lz4d_legacy = env_int("B2S_LZ4D_LEGACY", 0);
+  g_lz4d_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4D_CHUNK_BLOCKS", (int)g_lz4d_chunk_blocks));
   g_host_chunk_bytes = (uint64_t)std::max(1, env_int("B2S_HOST_CHUNK_MB", (int)(g_host_chunk_bytes >> 20))) << 20;
   Context* C = new Context();
   for (int d = 0; d < count && d < 32; d++) {

@@ -40,14 +40,17 @@ __global__ void __launch_bounds__(64) lz4_tokens_kernel(const BlockDesc* __restr
   int ip = 0, op = 0;
   uint32_t ns = 0;
   bool err = false;
-  if (clen > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + 128));
+  int pf_sector = -1;
+  for (int k = 64; k < 512 && k < clen; k += 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + k));
   for (;;) {
     if (ip >= clen) {
       err = true;
       break;
     }
-    if ((ip & 31) < 4 && ip + 256 < clen)  // ~once per 32-byte sector: each lane streams its own block
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(in + ip + 256));
+    if ((ip >> 5) != pf_sector) {  // entering a new 32-byte sector: each lane streams its own block, so pull the
+      pf_sector = ip >> 5;         // sector 16 ahead towards L1/L2 now (a miss is a DRAM round trip otherwise)
+      if (ip + 512 < clen) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + ip + 512));
+    }
     const int token = __ldg(in + ip++);
     int ll = token >> 4;
     if (ll == 15) {
