@@ -1,2 +1,2 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r1p.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_under_ncu_r1p.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"lz4_match" -c 1 -o gpurun_out/match_r1p python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu_match_r1p.log 2>&1
+python -m pytest tests -m gpu -q 2>&1 | tail -15
+python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print(b['value'], b['kernels'])"
