@@ -14,7 +14,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200shuffle.so")
 HOST_LIB = os.path.join(HERE, "libb200shuffle_host.so")
 HOST_SRC = os.path.join(HERE, "host", "shuffle_host.cpp")
-SOURCES = ["api.cu", "scan.cu", "checksum.cu", "xxh32.cu", "lz4.cu", "lz4_compress.cu", "lz4_decode.cu", "snappy.cu", "zstd.cu", "gen.cu"]
+SOURCES = ["api.cu", "scan.cu", "checksum.cu", "xxh32.cu", "lz4.cu", "lz4_compress.cu", "lz4_decode.cu", "snappy.cu", "zstd.cu", "zstd_enc.cu", "gen.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

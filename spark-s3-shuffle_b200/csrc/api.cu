@@ -149,6 +149,7 @@ struct Device {
   int ordinal = 0;
   Slot slot[NSLOT];
   ChecksumTables tabs{};
+  void* zstd_ctables = nullptr;  // predefined FSE compression tables (zstd_enc.cu)
   std::mutex mtx;
 };
 
@@ -195,7 +196,9 @@ struct WallTimer {
 // compress job: one chunk of n streams living in a device source arena
 // --------------------------------------------------------------------------------------------------------------
 // bytes every stream adds around its codec blocks: LZ4Block end mark (21) / xerial stream header (16)
-inline uint64_t stream_overhead(uint32_t codec) { return codec == B2S_CODEC_SNAPPY_XERIAL ? 16ull : 21ull; }
+inline uint64_t stream_overhead(uint32_t codec) {
+  return codec == B2S_CODEC_SNAPPY_XERIAL ? 16ull : codec == B2S_CODEC_ZSTD ? 9ull : 21ull;  // + zstd: frame header 6 + end block 3
+}
 
 struct CompressJob {
   uint32_t n = 0, nb = 0, codec = 0;
@@ -211,10 +214,10 @@ struct CompressJob {
 
 // lays out pinned + device meta for a compress chunk; returns 0 or error
 int compress_prepare(Slot& S, uint32_t codec, uint32_t bs, uint32_t n, const uint64_t* src_len, CompressJob& J) {
-  if (codec != B2S_CODEC_LZ4BLOCK && codec != B2S_CODEC_SNAPPY_XERIAL)
-    return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", codec == B2S_CODEC_ZSTD ? "zstd" : "");
-  if (codec == B2S_CODEC_LZ4BLOCK && (bs < 64 || bs > 65536))
-    return fail(B2S_E_UNSUPPORTED, "lz4 block size must be in [64, 65536]%s");
+  if (codec != B2S_CODEC_LZ4BLOCK && codec != B2S_CODEC_SNAPPY_XERIAL && codec != B2S_CODEC_ZSTD)
+    return fail(B2S_E_UNSUPPORTED, "codec %s not supported by this build", "");
+  if (codec != B2S_CODEC_SNAPPY_XERIAL && (bs < 64 || bs > 65536))
+    return fail(B2S_E_UNSUPPORTED, "lz4 / zstd block size must be in [64, 65536]%s");
   if (codec == B2S_CODEC_SNAPPY_XERIAL && (bs < 64 || bs > 32768))
     return fail(B2S_E_UNSUPPORTED, "snappy block size must be in [64, 32768]%s");
   J.n = n;
@@ -328,7 +331,10 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
     CU(cudaEventRecord(S.ev_free[par], st));
   }
   CU(cudaEventRecord(S.ev_t1, st));
-  if (codec == B2S_CODEC_SNAPPY_XERIAL)
+  if (codec == B2S_CODEC_ZSTD)
+    launch_zstd_stream_meta(M.blk_base, n, nb, M.sizes, M.total, d_dst, dst_cap, M.dst_off, M.dst_len, M.status, st,
+                            launches);
+  else if (codec == B2S_CODEC_SNAPPY_XERIAL)
     launch_xerial_stream_meta(M.blk_base, n, nb, M.sizes, M.total, d_dst, dst_cap, M.dst_off, M.dst_len, M.status, st,
                               launches);
   else
@@ -662,6 +668,8 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
       for (auto p : evs) CU(cudaEventCreate(p));
     }
     if (checksum_tables_create(&D->tabs)) return fail(B2S_E_CUDA, "checksum table upload failed%s");
+    if (zstd_ctables_create(&D->zstd_ctables)) return fail(B2S_E_CUDA, "zstd table upload failed%s");
+    zstd_set_ctables(d, D->zstd_ctables);
     C->devs.push_back(D);
   }
   if (C->devs.empty()) {
@@ -698,6 +706,7 @@ void b2s_shutdown(void) {
       if (S.st) cudaStreamDestroy(S.st);
     }
     checksum_tables_destroy(&D->tabs);
+    zstd_ctables_destroy(D->zstd_ctables);
     delete D;
   }
   delete g_ctx;
@@ -732,7 +741,7 @@ uint64_t b2s_compress_bound(uint32_t codec, uint32_t codec_block_size, uint64_t 
   switch (codec) {
     case B2S_CODEC_LZ4BLOCK: return src_len + (nb + 1) * 21;  // RAW fallback bounds every block by its input
     case B2S_CODEC_SNAPPY_XERIAL: return 16 + nb * 37 + src_len + src_len / 6;  // per chunk: BE32 + 32 + n + n/6
-    case B2S_CODEC_ZSTD: return src_len + (src_len >> 8) + 64 + nb * 32;
+    case B2S_CODEC_ZSTD: return src_len + nb * 3 + 9;  // Raw_Block fallback bounds every block by its input
     default: return src_len;
   }
 }

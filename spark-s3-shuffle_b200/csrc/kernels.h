@@ -121,6 +121,24 @@ void launch_zstd_decode(const uint8_t* src_base, const uint64_t* d_src_off, cons
                         uint8_t* d_ws, uint64_t* d_olen, uint8_t* dst_base, const uint64_t* d_dst_off, uint64_t dst_cap,
                         int32_t* d_status, cudaStream_t st, uint64_t* launches);
 
+// ---------------- zstd_enc.cu (K7: Zstandard frame encoding: raw literals + predefined-FSE sequences) ----------------
+int zstd_ctables_create(void** d_tables);  // predefined FSE compression tables, on the current device
+void zstd_ctables_destroy(void* d_tables);
+void zstd_set_ctables(int ordinal, const void* d_tables);
+void launch_zstd_seqenc(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                        const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+                        uint32_t stride, uint32_t max_seq, const uint16_t* d_off, const uint2* d_seq,
+                        const uint32_t* d_nseq, uint8_t* d_bits, uint32_t* d_nbits, uint32_t* d_csize,
+                        uint64_t* d_sizes, cudaStream_t st, uint64_t* launches);
+void launch_zstd_emit(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                      const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+                      uint32_t stride, uint32_t max_seq, const uint2* d_seq, const uint32_t* d_nseq,
+                      const uint8_t* d_bits, const uint32_t* d_nbits, const uint32_t* d_csize, const uint64_t* d_scan,
+                      uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches);
+void launch_zstd_stream_meta(const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, const uint64_t* d_scan,
+                             const uint64_t* d_scan_total, uint8_t* dst_base, uint64_t dst_cap, uint64_t* d_dst_off,
+                             uint64_t* d_dst_len, int32_t* d_status, cudaStream_t st, uint64_t* launches);
+
 // ---------------- gen.cu (bench utility) ----------------
 void launch_gen_terasort(uint8_t* d_dst, uint64_t first_record, uint64_t n_records, uint64_t seed, cudaStream_t st);
 

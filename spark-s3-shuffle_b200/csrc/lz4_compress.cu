@@ -265,13 +265,16 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match_kernel(
 // The walk is a fixed-trip loop over groups of 4 positions (one 64-bit load of ml[], next group prefetched).  A match
 // is at least 4 long, so at most one sequence starts per group: every iteration is the same straight-line code for
 // all 32 lanes (= 32 blocks), no source access, no data-dependent trip counts.
-// SNAPPY = true: same walk, Snappy element sizes (no RAW fallback, varint preamble, copies split at 64 bytes).
-template <bool SNAPPY>
+// CODEC: 0 = LZ4; 1 = Snappy: same walk, Snappy element sizes (no RAW fallback, varint preamble, copies split at 64
+// bytes); 2 = Zstandard: same walk, the record carries the running literal count instead of an output offset (sizes
+// are only known after the entropy stage, zstd_enc.cu) and the block's trailing literals become a final ml == 0 record.
+template <int CODEC>
 __global__ void __launch_bounds__(64) lz4_parse_kernel(
     const uint64_t* __restrict__ src_len, const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0,
     uint32_t m, uint32_t block_size, uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ mlarr,
     uint2* __restrict__ seqarr, uint32_t* __restrict__ nseq, uint32_t* __restrict__ csize,
     uint64_t* __restrict__ sizes) {
+  constexpr bool SNAPPY = CODEC == 1, ZSTD = CODEC == 2;
   const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= m) return;
   const uint32_t b = b0 + bl;
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
   const uint64_t rem = src_len[si] - (uint64_t)(b - blk_base[si]) * block_size;
   const int n = (int)(rem < block_size ? rem : block_size);
   // LZ4BlockOutputStream stores RAW when compressedLength >= originalLength; SnappyOutputStream never does
-  const int cap = SNAPPY ? 0x7fffffff : n - 1;
+  const int cap = (SNAPPY || ZSTD) ? 0x7fffffff : n - 1;
   const unsigned long long* __restrict__ mlw =
       reinterpret_cast<const unsigned long long*>(mlarr + (size_t)bl * stride);
   uint2* __restrict__ seq = seqarr + (size_t)bl * max_seq;
@@ -316,7 +319,9 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
           p = base + idx;
           const int lit = p - anchor;
           int size;
-          if (SNAPPY) {
+          if (ZSTD) {
+            size = lit;  // "op" counts literal bytes: where this sequence's literals go in the literals section
+          } else if (SNAPPY) {
             size = lit ? lit + (lit - 1 < 60 ? 1 : lit - 1 < 256 ? 2 : 3) : 0;
             int len = ml;
             if (len >= 68) {
@@ -349,6 +354,11 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
       }
       if (fail) break;
     }
+  }
+  if (ZSTD) {  // trailing literals as a final ml == 0 record; sizes are decided by the entropy stage
+    seq[ns++] = make_uint2((uint32_t)anchor | ((uint32_t)(n - anchor) << 16), (uint32_t)op << 16);
+    nseq[b] = ns;
+    return;
   }
   if (SNAPPY) {
     const int lit = n - anchor;
@@ -523,7 +533,8 @@ static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, c
 size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size) {
   const size_t stride = (block_size + 31u) & ~31u;
   const size_t max_seq = stride / 4 + 2;
-  return (size_t)chunk_blocks * (stride * 4 + max_seq * 8) + 1024;
+  // off + ml (4 B / position), records, and (Zstandard only, always reserved) one byte per position of bitstream
+  return (size_t)chunk_blocks * (stride * 4 + max_seq * 8 + stride + 32) + 1024;
 }
 
 struct Lz4Ws {
@@ -571,8 +582,21 @@ void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, c
                            uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches) {
   if (!m) return;
   const Lz4Ws w = carve_ws(d_ws, m, block_size);
+  if (codec == B2S_CODEC_ZSTD) {
+    lz4_parse_kernel<2><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
+                                                      w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+    uint8_t* d_bits = d_ws + (size_t)m * w.stride * 4 + (size_t)m * w.max_seq * 8;
+    // d_hash is unused by this codec and carries the bitstream sizes from the entropy stage to the emit kernel
+    launch_zstd_seqenc(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq,
+                       w.off, w.seq, d_nseq, d_bits, const_cast<uint32_t*>(d_hash), d_csize, d_sizes, st, launches);
+    launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);
+    launch_zstd_emit(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq,
+                     w.seq, d_nseq, d_bits, d_hash, d_csize, d_sizes, dst_base, dst_cap, st, launches);
+    *launches += 1;
+    return;
+  }
   if (codec == B2S_CODEC_SNAPPY_XERIAL) {
-    lz4_parse_kernel<true><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
+    lz4_parse_kernel<1><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
                                                          w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
     launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);
     launch_snappy_emit(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq,
@@ -580,7 +604,7 @@ void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, c
     *launches += 1;
     return;
   }
-  lz4_parse_kernel<false><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
+  lz4_parse_kernel<0><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
                                                         w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
   // packed offsets of this chunk's blocks, chained onto the running total of the chunks before it
   launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);

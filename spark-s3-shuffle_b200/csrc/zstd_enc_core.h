@@ -1,0 +1,280 @@
+// zstd_enc_core.h — Zstandard (RFC 8878) block ENCODING helpers, written once for host and device.
+//
+// Replaces, for spark.io.compression.codec=zstd on the write side, com.github.luben.zstd.ZstdOutputStreamNoFinalizer [U]
+// (zstd-jni -> libzstd ZSTD_compressStream2).  Deliberately simple, valid-first encoder (SURVEY.md §7 "hard parts":
+// staged encoder, valid frames first, ratio second): matches come from the shared LZ match finder, a block is
+//   Raw_Literals section  +  sequences coded with the PREDEFINED FSE distributions (no table descriptions, no Huffman),
+// or a Raw_Block when that is not smaller.  Any conforming decoder — libzstd / zstd-jni included — reads it.
+// The same functions are compiled into zstd_enc.cu (product) and into the host unit test (tests/native), where the
+// frames they produce are decoded by libzstd.so.1.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2S_HD __host__ __device__
+#else
+#ifndef B2S_HD
+#define B2S_HD
+#endif
+#endif
+
+namespace b2s {
+namespace zstdenc {
+
+// ---- FSE compression tables for the three predefined distributions (RFC 8878 3.1.1.3.2.2) ---------------------------
+struct SymbolTT {
+  int32_t deltaFindState;
+  uint32_t deltaNbBits;
+};
+struct CTables {  // ~2.4 KB; built once on the host, uploaded to the device
+  uint16_t ll_state[64], of_state[32], ml_state[64];
+  SymbolTT ll_tt[36], of_tt[29], ml_tt[53];
+};
+
+inline int hb32(uint32_t v) {
+  int r = 0;
+  while (v >>= 1) r++;
+  return r;
+}
+
+// FSE_buildCTable for one distribution (host only; runs once)
+inline void build_ctable(const int16_t* norm, int nsym, int log, uint16_t* stateTable, SymbolTT* tt) {
+  const int size = 1 << log;
+  uint8_t sym[64];
+  int cumul[64 + 1];
+  int high = size - 1;
+  cumul[0] = 0;
+  for (int u = 1; u <= nsym; u++) {
+    if (norm[u - 1] == -1) {
+      cumul[u] = cumul[u - 1] + 1;
+      sym[high--] = (uint8_t)(u - 1);
+    } else {
+      cumul[u] = cumul[u - 1] + norm[u - 1];
+    }
+  }
+  const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+  int pos = 0;
+  for (int s = 0; s < nsym; s++)
+    for (int i = 0; i < norm[s]; i++) {
+      sym[pos] = (uint8_t)s;
+      do pos = (pos + step) & mask;
+      while (pos > high);
+    }
+  for (int u = 0; u < size; u++) {
+    const int s = sym[u];
+    stateTable[cumul[s]++] = (uint16_t)(size + u);
+  }
+  int total = 0;
+  for (int s = 0; s < nsym; s++) {
+    const int n = norm[s];
+    if (n == 0) {
+      tt[s].deltaNbBits = (uint32_t)(((log + 1) << 16) - (1 << log));
+      tt[s].deltaFindState = 0;
+    } else if (n == -1 || n == 1) {
+      tt[s].deltaNbBits = (uint32_t)((log << 16) - (1 << log));
+      tt[s].deltaFindState = total - 1;
+      total++;
+    } else {
+      const int maxBitsOut = log - hb32((uint32_t)(n - 1));
+      const int minStatePlus = n << maxBitsOut;
+      tt[s].deltaNbBits = (uint32_t)((maxBitsOut << 16) - minStatePlus);
+      tt[s].deltaFindState = total - n;
+      total += n;
+    }
+  }
+}
+
+inline void build_predefined(CTables* t) {
+  const int16_t LL[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
+  const int16_t OF[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
+  const int16_t ML[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                          1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
+  build_ctable(LL, 36, 6, t->ll_state, t->ll_tt);
+  build_ctable(OF, 29, 5, t->of_state, t->of_tt);
+  build_ctable(ML, 53, 6, t->ml_state, t->ml_tt);
+}
+
+// ---- symbol codes ---------------------------------------------------------------------------------------------------
+B2S_HD inline int highbit(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(v);
+#else
+  int r = 0;
+  while (v >>= 1) r++;
+  return r;
+#endif
+}
+// literal length -> code, extra bits, extra value
+B2S_HD inline void ll_encode(uint32_t ll, int* code, int* nbits, uint32_t* extra) {
+  int c;
+  if (ll < 16) c = (int)ll;
+  else if (ll < 64) {
+    // 16,16,17,17,18,18,19,19,20,20,20,20,21,21,21,21,22 x8,23 x8,24 x16
+    c = ll < 24 ? 16 + (int)((ll - 16) >> 1) : ll < 32 ? 20 + (int)((ll - 24) >> 2) : ll < 48 ? 22 + (int)((ll - 32) >> 3) : 24;
+  } else {
+    c = highbit(ll) + 19;
+  }
+  const uint32_t base[36] = {0,  1,  2,  3,  4,  5,  6,  7,  8,   9,   10,  11,   12,   13,   14,   15,    16,    18,
+                             20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
+  const uint8_t bits[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+  *code = c;
+  *nbits = bits[c];
+  *extra = ll - base[c];
+}
+// match length (>= 3) -> code, extra bits, extra value
+B2S_HD inline void ml_encode(uint32_t ml, int* code, int* nbits, uint32_t* extra) {
+  const uint32_t mb = ml - 3;
+  int c;
+  if (mb < 32) c = (int)mb;
+  else if (mb < 128) {
+    // 32,32,33,33,34,34,35,35,36 x4,37 x4,38 x8,39 x8,40 x16,41 x16,42 x32
+    c = mb < 40 ? 32 + (int)((mb - 32) >> 1) : mb < 48 ? 36 + (int)((mb - 40) >> 2) : mb < 64 ? 38 + (int)((mb - 48) >> 3)
+        : mb < 96 ? 40 + (int)((mb - 64) >> 4) : 42;
+  } else {
+    c = highbit(mb) + 36;
+  }
+  const uint32_t base[53] = {3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20,
+                             21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41,
+                             43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
+  const uint8_t bits[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                            0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+  *code = c;
+  *nbits = bits[c];
+  *extra = ml - base[c];
+}
+
+// ---- forward bit writer (the sequence bitstream is written forwards, sequences in reverse order) ------------------
+struct BitWriter {
+  uint8_t* p;
+  uint32_t cap, n;  // bytes written so far; overflow => n stays > cap
+  uint64_t acc;
+  int fill;
+  B2S_HD void init(uint8_t* dst, uint32_t capacity) {
+    p = dst;
+    cap = capacity;
+    n = 0;
+    acc = 0;
+    fill = 0;
+  }
+  B2S_HD void add(uint32_t v, int nb) {  // nb <= 24 per call
+    acc |= (uint64_t)(v & ((1u << nb) - 1u)) << fill;
+    fill += nb;
+    while (fill >= 8) {
+      if (n < cap) p[n] = (uint8_t)acc;
+      n++;
+      acc >>= 8;
+      fill -= 8;
+    }
+  }
+  B2S_HD void close() {  // final 1-bit marker
+    add(1, 1);
+    if (fill) {
+      if (n < cap) p[n] = (uint8_t)acc;
+      n++;
+      fill = 0;
+    }
+  }
+};
+
+struct FseState {
+  uint32_t v;
+};
+B2S_HD inline void fse_init(FseState* s, const uint16_t* st, const SymbolTT* tt, int sym) {
+  const uint32_t nb = (tt[sym].deltaNbBits + (1u << 15)) >> 16;
+  const uint32_t value = (nb << 16) - tt[sym].deltaNbBits;
+  s->v = st[(value >> nb) + tt[sym].deltaFindState];
+}
+B2S_HD inline void fse_encode(BitWriter* bw, FseState* s, const uint16_t* st, const SymbolTT* tt, int sym) {
+  const uint32_t nb = (s->v + tt[sym].deltaNbBits) >> 16;
+  bw->add(s->v, (int)nb);
+  s->v = st[(s->v >> nb) + tt[sym].deltaFindState];
+}
+
+// One sequence as the encoder sees it
+struct Seq {
+  uint32_t ll, ml, off;  // literal length, match length (>= 4 here), real offset (>= 1)
+};
+
+// Encodes `nseq` sequences (get(i) returns sequence i, 0 <= i < nseq, in parse order) into dst; returns the byte
+// count, or cap + 1 when it does not fit.
+template <typename Get>
+B2S_HD inline uint32_t encode_sequences(const CTables* T, uint32_t nseq, Get get, uint8_t* dst, uint32_t cap) {
+  BitWriter bw;
+  bw.init(dst, cap);
+  FseState sl, so, sm;
+  int lc, ln, mc, mn;
+  uint32_t le, me;
+  {
+    const Seq q = get(nseq - 1);
+    const uint32_t ofv = q.off + 3;
+    const int oc = highbit(ofv);
+    ll_encode(q.ll, &lc, &ln, &le);
+    ml_encode(q.ml, &mc, &mn, &me);
+    fse_init(&sm, T->ml_state, T->ml_tt, mc);
+    fse_init(&so, T->of_state, T->of_tt, oc);
+    fse_init(&sl, T->ll_state, T->ll_tt, lc);
+    bw.add(le, ln);
+    bw.add(me, mn);
+    bw.add(ofv - (1u << oc), oc);
+  }
+  for (uint32_t i = nseq - 1; i-- > 0;) {
+    const Seq q = get(i);
+    const uint32_t ofv = q.off + 3;
+    const int oc = highbit(ofv);
+    ll_encode(q.ll, &lc, &ln, &le);
+    ml_encode(q.ml, &mc, &mn, &me);
+    fse_encode(&bw, &so, T->of_state, T->of_tt, oc);
+    fse_encode(&bw, &sm, T->ml_state, T->ml_tt, mc);
+    fse_encode(&bw, &sl, T->ll_state, T->ll_tt, lc);
+    bw.add(le, ln);
+    bw.add(me, mn);
+    bw.add(ofv - (1u << oc), oc);
+    if (bw.n > cap) return cap + 1;
+  }
+  bw.add(sm.v, 6);
+  bw.add(so.v, 5);
+  bw.add(sl.v, 6);
+  bw.close();
+  return bw.n > cap ? cap + 1 : bw.n;
+}
+
+// ---- headers -----------------------------------------------------------------------------------------------------
+constexpr uint32_t kFrameHeaderBytes = 6;  // magic + Frame_Header_Descriptor (no FCS, no dict, no checksum) + window
+constexpr uint32_t kEndBlockBytes = 3;     // every stream ends with an empty Raw_Block carrying Last_Block
+B2S_HD inline void put_frame_header(uint8_t* p) {
+  p[0] = 0x28; p[1] = 0xB5; p[2] = 0x2F; p[3] = 0xFD;
+  p[4] = 0x00;  // FCS flag 0, single segment 0, no checksum, no dictionary
+  p[5] = 0x38;  // window descriptor: exponent 7, mantissa 0 -> 128 KiB (>= any offset a <= 64 KiB block produces)
+}
+B2S_HD inline void put_block_header(uint8_t* p, int last, int type, uint32_t size) {
+  const uint32_t v = (uint32_t)last | ((uint32_t)type << 1) | (size << 3);
+  p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16);
+}
+B2S_HD inline uint32_t raw_literals_header_bytes(uint32_t n) { return n < 32 ? 1 : n < 4096 ? 2 : 3; }
+B2S_HD inline void put_raw_literals_header(uint8_t* p, uint32_t n) {
+  if (n < 32) {
+    p[0] = (uint8_t)(n << 3);
+  } else if (n < 4096) {
+    const uint32_t v = (n << 4) | (1u << 2);
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8);
+  } else {
+    const uint32_t v = (n << 4) | (3u << 2);
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16);
+  }
+}
+B2S_HD inline uint32_t nseq_header_bytes(uint32_t nseq) { return nseq < 128 ? 1 : nseq < 0x7F00 ? 2 : 3; }
+B2S_HD inline void put_nseq(uint8_t* p, uint32_t nseq) {
+  if (nseq < 128) {
+    p[0] = (uint8_t)nseq;
+  } else if (nseq < 0x7F00) {
+    p[0] = (uint8_t)((nseq >> 8) + 128);
+    p[1] = (uint8_t)nseq;
+  } else {
+    p[0] = 255;
+    p[1] = (uint8_t)(nseq - 0x7F00);
+    p[2] = (uint8_t)((nseq - 0x7F00) >> 8);
+  }
+}
+
+}  // namespace zstdenc
+}  // namespace b2s

@@ -20,3 +20,109 @@ long long zc_size(const unsigned char* src, unsigned long long n) {
 }
 unsigned long long zc_workspace_bytes() { return sizeof(b2s::zstd::Workspace); }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// CPU model of the GPU Zstandard ENCODER (zstd_enc.cu): the shared window match finder + greedy parse (the same
+// specification as orc_lz4_compress_block_win in oracle/), then the encoder core of zstd_enc_core.h.
+// ------------------------------------------------------------------------------------------------------------------
+#include <string.h>
+
+#include <vector>
+
+#include "../../spark-s3-shuffle_b200/csrc/zstd_enc_core.h"
+
+namespace {
+inline uint32_t rd32(const uint8_t* p) {
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return v;
+}
+// phase A of the GPU compressor: fixed windows of 32 positions, table state before the window, offset-1 for byte runs
+void win_find_offsets(const uint8_t* src, int n, int hash_log, std::vector<uint16_t>& off) {
+  std::vector<uint16_t> table((size_t)1 << hash_log, 0);
+  const int mflimit = n - 12;
+  for (int pos = 0; pos <= mflimit; pos += 32) {
+    const int last = pos + 31 < mflimit ? pos + 31 : mflimit;
+    for (int p = pos; p <= last; p++) {
+      const uint32_t v = rd32(src + p);
+      const int c = table[(v * 2654435761u) >> (32 - hash_log)];
+      if (p > 0 && rd32(src + p - 1) == v) off[p] = 1;
+      else if (c < p && rd32(src + c) == v) off[p] = (uint16_t)(p - c);
+    }
+    for (int p = pos; p <= last; p++) table[(rd32(src + p) * 2654435761u) >> (32 - hash_log)] = (uint16_t)p;
+  }
+}
+}  // namespace
+
+extern "C" long long zc_compress_model(const unsigned char* src, unsigned long long n, unsigned block_size,
+                                       unsigned char* dst, unsigned long long cap) {
+  using namespace b2s::zstdenc;
+  static CTables T;
+  static bool built = false;
+  if (!built) {
+    build_predefined(&T);
+    built = true;
+  }
+  unsigned long long op = 0;
+  if (cap < kFrameHeaderBytes + kEndBlockBytes) return -3;
+  put_frame_header(dst);
+  op = kFrameHeaderBytes;
+  std::vector<uint8_t> lits, bits;
+  for (unsigned long long b0 = 0; b0 < n; b0 += block_size) {
+    const int bn = (int)(n - b0 < block_size ? n - b0 : block_size);
+    const uint8_t* s = src + b0;
+    std::vector<Seq> seqs;
+    lits.clear();
+    int anchor = 0;
+    if (bn >= 13) {
+      std::vector<uint16_t> off((size_t)bn, 0);
+      win_find_offsets(s, bn, 12, off);
+      const int mflimit = bn - 12, matchlimit = bn - 5;
+      int p = 0;
+      while (p <= mflimit) {
+        if (!off[p]) {
+          p++;
+          continue;
+        }
+        const int c = p - off[p];
+        int ml = 4;
+        while (p + ml < matchlimit && s[p + ml] == s[c + ml]) ml++;
+        seqs.push_back(Seq{(uint32_t)(p - anchor), (uint32_t)ml, off[p]});
+        lits.insert(lits.end(), s + anchor, s + p);
+        p += ml;
+        anchor = p;
+      }
+    }
+    lits.insert(lits.end(), s + anchor, s + bn);
+    // compressed block: raw literals + predefined-FSE sequences, when smaller than the raw block
+    bool raw = seqs.empty();
+    uint32_t csize = 0, nbits = 0;
+    if (!raw) {
+      bits.assign((size_t)bn + 16, 0);
+      nbits = encode_sequences(&T, (uint32_t)seqs.size(), [&](uint32_t i) { return seqs[i]; }, bits.data(), (uint32_t)bn);
+      csize = raw_literals_header_bytes((uint32_t)lits.size()) + (uint32_t)lits.size() + nseq_header_bytes((uint32_t)seqs.size()) + 1 + nbits;
+      if (nbits > (uint32_t)bn || csize >= (uint32_t)bn) raw = true;
+    }
+    const uint32_t payload = raw ? (uint32_t)bn : csize;
+    if (op + 3 + payload + kEndBlockBytes > cap) return -3;
+    put_block_header(dst + op, 0, raw ? 0 : 2, payload);
+    op += 3;
+    if (raw) {
+      memcpy(dst + op, s, (size_t)bn);
+    } else {
+      uint8_t* q = dst + op;
+      put_raw_literals_header(q, (uint32_t)lits.size());
+      q += raw_literals_header_bytes((uint32_t)lits.size());
+      memcpy(q, lits.data(), lits.size());
+      q += lits.size();
+      put_nseq(q, (uint32_t)seqs.size());
+      q += nseq_header_bytes((uint32_t)seqs.size());
+      *q++ = 0;  // predefined LL / OF / ML
+      memcpy(q, bits.data(), nbits);
+    }
+    op += payload;
+  }
+  put_block_header(dst + op, 1, 0, 0);  // empty Raw_Block with Last_Block
+  op += kEndBlockBytes;
+  return (long long)op;
+}

@@ -73,3 +73,79 @@ def test_many_shuffle_blocks_packed(capi, oracle):
     r = capi.decompress_packed(capi.CODEC_ZSTD, src, off, ln, dst)
     assert not r["status"].any() and r["total"] == total
     assert dst.tobytes() == b"".join(parts)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# write side: the GPU encoder (raw literals + predefined-FSE sequences) against its CPU model and against libzstd
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def zmodel(tmp_path_factory):
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path_factory.mktemp("zc") / "libzc.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out,
+                           os.path.join(root, "tests", "native", "zstd_core_host.cpp")])
+    L = C.CDLL(out)
+    L.zc_compress_model.restype = C.c_longlong
+    L.zc_compress_model.argtypes = [C.c_char_p, C.c_ulonglong, C.c_uint, C.c_char_p, C.c_ulonglong]
+
+    def model(data, block_size=32768):
+        cap = len(data) + len(data) // 64 + 1024
+        buf = C.create_string_buffer(cap)
+        n = L.zc_compress_model(data, len(data), block_size, buf, cap)
+        assert n > 0
+        return buf.raw[:n]
+    return model
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_gpu_zstd_encode_equals_cpu_model_and_libzstd_decodes_it(capi, oracle, zmodel, kind):
+    sizes = [0, 1, 12, 13, 100, 1000, 32767, 32768, 32769, 70001, 300000]
+    parts = [corpus(oracle, kind, n, seed=i) for i, n in enumerate(sizes)]
+    comp, cks, st = capi.compress_batch(capi.CODEC_ZSTD, parts, 32768, capi.CHECKSUM_CRC32C)
+    assert st == [0] * len(parts)
+    for p, f, k in zip(parts, comp, cks):
+        assert zstd_ref.decompress(f) == p, "libzstd cannot read the GPU-written frame"
+        assert f == zmodel(p), "kernel output differs from its CPU model"
+        assert k == oracle.crc32c(f)
+    # and back through the GPU decoder
+    out, st, _ = capi.decompress_batch(capi.CODEC_ZSTD, comp)
+    assert st == [0] * len(parts) and out == parts
+
+
+@pytest.mark.parametrize("bs", [64, 4096, 65536])
+def test_gpu_zstd_block_size_sweep(capi, oracle, zmodel, bs):
+    p = corpus(oracle, "text", 200000, 3) + corpus(oracle, "terasort", 100000, 4)
+    comp, _, st = capi.compress_batch(capi.CODEC_ZSTD, [p], bs)
+    assert st == [0] and zstd_ref.decompress(comp[0]) == p and comp[0] == zmodel(p, bs)
+
+
+def test_host_mirror_with_zstd_codec(tmp_path, oracle):
+    import uuid
+    import spark_s3_shuffle_b200 as pkg
+    from shuffle_model import decode_pairs, encode_pairs
+    host = pkg.host
+    d = host.S3ShuffleDispatcher({"spark.app.id": "app-" + uuid.uuid4().hex[:8],
+                                  "spark.shuffle.s3.rootDir": "file://" + str(tmp_path) + "/s",
+                                  "spark.io.compression.codec": "zstd"})
+    i = np.arange(80000, dtype=np.int64)
+    w = host.S3ShuffleMapOutputWriter(d, 0, 0, 3)
+    for r in range(3):
+        with w.getPartitionWriter(r) as s:
+            s.write(encode_pairs(i[i % 3 == r] % 40, i[i % 3 == r]))
+    lens = w.commitAllPartitions()
+    w.close()
+    # the unmodified reference's reduce side = libzstd over the partition's byte range
+    data = open(d.getPath("data", 0, 0), "rb").read()
+    acc = np.concatenate(([0], np.cumsum(lens)))
+    for r in range(3):
+        dec = zstd_ref.decompress(data[int(acc[r]):int(acc[r + 1])])
+        assert np.array_equal(decode_pairs(dec)[1], i[i % 3 == r])
+    rd = host.S3ShuffleReader(d, 0, [0], 0, 3, False)
+    blocks = rd.read()
+    v = np.concatenate([decode_pairs(b)[1] for _, b in blocks])
+    assert np.array_equal(np.sort(v), i)
+    rd.close()
+    d.close()

@@ -92,3 +92,23 @@ def test_bit_flips_never_crash_and_agree_with_libzstd_when_it_rejects(zc, oracle
         elif r >= 0 and ref is None:
             accepted_wrong += 1        # we accepted what libzstd rejects (no checksum in the frame: tolerated, counted)
     assert accepted_wrong <= 30
+
+
+def test_encoder_model_frames_are_read_by_libzstd(zc, oracle):
+    """zstd_enc_core.h (raw literals + predefined-FSE sequences) through the CPU model of the GPU encoder: libzstd and
+    our own decoder core both reproduce the input; incompressible blocks fall back to Raw_Block."""
+    zc.zc_compress_model.restype = C.c_longlong
+    zc.zc_compress_model.argtypes = [C.c_char_p, C.c_ulonglong, C.c_uint, C.c_char_p, C.c_ulonglong]
+    for kind in KINDS:
+        for n in (0, 1, 12, 13, 100, 1000, 32768, 32769, 100000, 300000):
+            for bs in (32768, 65536, 1000):
+                d = corpus(oracle, kind, n, seed=1)
+                cap = n + n // 64 + 9 + 3 * (n // bs + 2)
+                buf = C.create_string_buffer(cap)
+                c = zc.zc_compress_model(d, n, bs, buf, cap)
+                assert 9 <= c <= cap
+                f = buf.raw[:c]
+                assert zstd_ref.decompress(f) == d
+                r, out = decode(zc, f, n)
+                assert r == n and out == d
+    assert zc.zc_compress_model(b"", 0, 32768, buf, cap) == 9   # frame header + empty last block

@@ -1,2 +1,1 @@
 python -m pytest tests -m gpu -q 2>&1 | tail -15
-python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print(b['value'], b['kernels'])"
