@@ -117,6 +117,8 @@ def main():
     ap.add_argument("--cpu-sample-blocks", type=int, default=6000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--codec", default="lz4", choices=["lz4", "snappy", "zstd"],
+                    help="lz4 = the BASELINE configuration; snappy / zstd report the other codecs on the same data")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -128,7 +130,11 @@ def main():
     total = n * block_bytes
     workload = "terasort %.2f GiB/GPU, %d shuffle blocks x %d B (80 maps x 200 partitions), LZ4Block 32 KiB + CRC32C" % (
         total / 2**30, n, block_bytes)
-    config = {"workload": workload, "codec": "lz4 (LZ4Block, blockSize 32 KiB)", "checksum": "CRC32C over compressed bytes",
+    codec_desc = {"lz4": "lz4 (LZ4Block, blockSize 32 KiB)", "snappy": "snappy (xerial framing, blockSize 32 KiB)",
+                  "zstd": "zstd (frames of 32 KiB blocks; raw literals + predefined-FSE sequences)"}[args.codec]
+    if args.codec != "lz4":
+        workload = workload.replace("LZ4Block 32 KiB", codec_desc)
+    config = {"workload": workload, "codec": codec_desc, "checksum": "CRC32C over compressed bytes",
               "blocks_per_gpu": n, "block_bytes": block_bytes, "l2_policy": "inputs (>= 6 GiB per pass) far larger than the 126 MB L2",
               "sharding": "block i -> GPU i mod N (each rank owns its blocks; no collective on the data path)"}
 
@@ -174,7 +180,8 @@ def main():
     L = c.load()
     barrier, max_over_ranks = rk.barrier, rk.max_over_ranks
 
-    cmp_cap = int(c.compress_bound(c.CODEC_LZ4BLOCK, LZ4_BLOCK, block_bytes)) * n
+    CODEC = {"lz4": c.CODEC_LZ4BLOCK, "snappy": c.CODEC_SNAPPY_XERIAL, "zstd": c.CODEC_ZSTD}[args.codec]
+    cmp_cap = int(c.compress_bound(CODEC, LZ4_BLOCK, block_bytes)) * n
     d_src, d_cmp, d_out = c.dev_alloc(total), c.dev_alloc(cmp_cap), c.dev_alloc(total)
     c.gen_terasort_dev(d_src, rank * n * RECORDS_PER_BLOCK, n * RECORDS_PER_BLOCK, 42)
     off = np.arange(n, dtype=np.uint64) * block_bytes
@@ -185,9 +192,9 @@ def main():
           "match_launches": []}
 
     def step_device(record):
-        w = c.compress_dev(c.CODEC_LZ4BLOCK, d_src, off, ln, d_cmp, cmp_cap, LZ4_BLOCK, c.CHECKSUM_CRC32C)
+        w = c.compress_dev(CODEC, d_src, off, ln, d_cmp, cmp_cap, LZ4_BLOCK, c.CHECKSUM_CRC32C)
         tw = c.last_timing()
-        r = c.decompress_dev(c.CODEC_LZ4BLOCK, d_cmp, w["dst_off"], w["dst_len"], d_out, total, c.CHECKSUM_CRC32C, sb,
+        r = c.decompress_dev(CODEC, d_cmp, w["dst_off"], w["dst_len"], d_out, total, c.CHECKSUM_CRC32C, sb,
                              w["dst_len"], w["checksums"])
         tr = c.last_timing()
         if record:
@@ -209,10 +216,14 @@ def main():
     barrier()
     sampler.start()
     t0 = time.perf_counter()
+    c.mark(0)                      # CUDA events on the library's own stream (every call is synchronous)
     for _ in range(steps):
         step_device(True)
+    c.mark(1)
+    dev_elapsed = c.marks_elapsed_ms() * 1e-3
     barrier()
-    elapsed = max_over_ranks(time.perf_counter() - t0)
+    wall = time.perf_counter() - t0
+    elapsed = max_over_ranks(max(dev_elapsed, 0.0) if dev_elapsed > 0.5 * wall else wall)
     clocks = sampler.stop()
     launches = L.b2s_total_kernel_launches() - launches0
     ms_per_step = elapsed / steps * 1e3
@@ -258,9 +269,9 @@ def main():
         d_src = d_cmp = d_out = None
 
         def step_host():
-            w = c.compress_packed(c.CODEC_LZ4BLOCK, h_src.array, off, ln, h_cmp.array, LZ4_BLOCK, c.CHECKSUM_CRC32C)
+            w = c.compress_packed(CODEC, h_src.array, off, ln, h_cmp.array, LZ4_BLOCK, c.CHECKSUM_CRC32C)
             tw = c.last_timing()
-            r = c.decompress_packed(c.CODEC_LZ4BLOCK, h_cmp.array, w["dst_off"], w["dst_len"], h_out.array,
+            r = c.decompress_packed(CODEC, h_cmp.array, w["dst_off"], w["dst_len"], h_out.array,
                                     c.CHECKSUM_CRC32C, sb, w["dst_len"], w["checksums"])
             tr = c.last_timing()
             return w, r, tw, tr
@@ -291,7 +302,7 @@ def main():
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and args.codec == "lz4":
         threads = os.cpu_count() or 1
         sample_blocks = min(args.cpu_sample_blocks, n)
         sample = oracle.gen_terasort(0, sample_blocks * RECORDS_PER_BLOCK)

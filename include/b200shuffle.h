@@ -151,6 +151,10 @@ typedef struct b2s_timing {
   uint64_t dominant_launches;
 } b2s_timing;
 int b2s_last_timing(b2s_timing* out);
+/* CUDA-event stopwatch on the library's own stream of device dev_index (torch.cuda.Event only sees torch's stream):
+ * b2s_mark(dev, 0) ... calls ... b2s_mark(dev, 1); b2s_marks_elapsed_ms(dev, &ms) synchronises on mark 1 */
+int b2s_mark(uint32_t dev_index, uint32_t which);
+int b2s_marks_elapsed_ms(uint32_t dev_index, double* ms);
 uint64_t b2s_total_kernel_launches(void); /* process-wide counter since b2s_init */
 
 /* ---- synthetic workload generator for the benchmark (device-side TeraGen-style 104-byte records; not on the

@@ -65,6 +65,8 @@ PROTOTYPES = [
     ("b2s_dev_memcpy", C.c_int, [_u32, C.c_void_p, C.c_void_p, _u64, C.c_int]),
     ("b2s_last_timing", C.c_int, [C.POINTER(Timing)]),
     ("b2s_total_kernel_launches", _u64, []),
+    ("b2s_mark", C.c_int, [_u32, _u32]),
+    ("b2s_marks_elapsed_ms", C.c_int, [_u32, C.POINTER(C.c_double)]),
     ("b2s_gen_terasort_dev", C.c_int, [_u32, C.c_void_p, _u64, _u64, _u64]),
 ]
 SYMBOLS = [p[0] for p in PROTOTYPES]
@@ -114,6 +116,16 @@ def last_timing():
     t = Timing()
     load().b2s_last_timing(C.byref(t))
     return t.as_dict()
+
+
+def mark(which, dev=0):
+    _check(load().b2s_mark(dev, which), "b2s_mark")
+
+
+def marks_elapsed_ms(dev=0):
+    ms = C.c_double(0)
+    _check(load().b2s_marks_elapsed_ms(dev, C.byref(ms)), "b2s_marks_elapsed_ms")
+    return ms.value
 
 
 def compress_bound(codec, block_size, n):

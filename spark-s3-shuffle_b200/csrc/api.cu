@@ -150,6 +150,7 @@ struct Device {
   Slot slot[NSLOT];
   ChecksumTables tabs{};
   void* zstd_ctables = nullptr;  // predefined FSE compression tables (zstd_enc.cu)
+  cudaEvent_t ev_mark[2] = {nullptr, nullptr};  // b2s_mark stopwatch
   std::mutex mtx;
 };
 
@@ -670,6 +671,8 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
     if (checksum_tables_create(&D->tabs)) return fail(B2S_E_CUDA, "checksum table upload failed%s");
     if (zstd_ctables_create(&D->zstd_ctables)) return fail(B2S_E_CUDA, "zstd table upload failed%s");
     zstd_set_ctables(d, D->zstd_ctables);
+    CU(cudaEventCreate(&D->ev_mark[0]));
+    CU(cudaEventCreate(&D->ev_mark[1]));
     C->devs.push_back(D);
   }
   if (C->devs.empty()) {
@@ -707,6 +710,8 @@ void b2s_shutdown(void) {
     }
     checksum_tables_destroy(&D->tabs);
     zstd_ctables_destroy(D->zstd_ctables);
+    for (auto ev : D->ev_mark)
+      if (ev) cudaEventDestroy(ev);
     delete D;
   }
   delete g_ctx;
@@ -777,6 +782,27 @@ int b2s_last_timing(b2s_timing* out) {
   return 0;
 }
 uint64_t b2s_total_kernel_launches(void) { return g_ctx ? g_ctx->launches.load() : 0; }
+
+int b2s_mark(uint32_t dev_index, uint32_t which) {
+  Device* D;
+  int rc = get_device(dev_index, &D);
+  if (rc) return rc;
+  if (which > 1) return fail(B2S_E_ARG, "mark index must be 0 or 1%s");
+  // every entry point is synchronous, so an event on the first slot's stream brackets whatever ran in between
+  CU(cudaEventRecord(D->ev_mark[which], D->slot[0].st));
+  return 0;
+}
+int b2s_marks_elapsed_ms(uint32_t dev_index, double* ms) {
+  Device* D;
+  int rc = get_device(dev_index, &D);
+  if (rc) return rc;
+  if (!ms) return fail(B2S_E_ARG, "null argument%s");
+  CU(cudaEventSynchronize(D->ev_mark[1]));
+  float f = 0;
+  CU(cudaEventElapsedTime(&f, D->ev_mark[0], D->ev_mark[1]));
+  *ms = f;
+  return 0;
+}
 
 int b2s_gen_terasort_dev(uint32_t dev_index, void* d_dst, uint64_t first_record, uint64_t n_records, uint64_t seed) {
   Device* D;
