@@ -67,35 +67,37 @@ struct BitsFwd {
 };
 
 // ---- backward bit reader (Huffman streams, sequence bitstream): starts below the final 1-bit marker ----------
+// Keeps up to 64 upcoming bits in a register (`buf` holds stream bits [lo, lo+64), refilled with one 8-byte gather
+// when the cursor leaves it) so a read is a shift and a mask, not a fresh walk over memory.
 struct BitsRev {
   const uint8_t* p;
   int64_t n;
   int64_t pos;  // bits still unread; may go negative (over-read: zeros), checked by the callers
+  uint64_t buf;
+  int64_t lo;   // bit index of buf's bit 0 (multiple of 8; may be negative: bits below the stream start are zero)
+  B2S_HD void fill(int64_t want_lo) {  // buf := stream bits [want_lo, want_lo + 64)
+    lo = want_lo;
+    uint64_t v = 0;
+    const int64_t b = want_lo >> 3;  // arithmetic shift: negative byte indices read as zero
+    for (int i = 0; i < 8; i++) {
+      const int64_t k = b + i;
+      if (k >= 0 && k < n) v |= (uint64_t)p[k] << (8 * i);
+    }
+    buf = v;
+  }
   B2S_HD bool init(const uint8_t* src, uint64_t len) {
     p = src;
     n = (int64_t)len;
     if (len == 0 || src[len - 1] == 0) return false;
     pos = (int64_t)(len - 1) * 8 + highbit32(src[len - 1]);
+    fill(((pos - 57) >> 3) * 8);  // pos lies within the top byte of the buffer
     return true;
   }
   B2S_HD uint32_t read(int nb) {  // nb <= 32
     if (nb == 0) return 0;
     pos -= nb;
-    int64_t bp = pos;
-    int shift = 0;
-    int take = nb;
-    if (bp < 0) {  // bits below the start of the stream read as zero
-      shift = (int)(-bp);
-      if (shift >= nb) return 0;
-      take = nb - shift;
-      bp = 0;
-    }
-    uint64_t v = 0;
-    const int64_t b = bp >> 3;
-    for (int i = 0; i < 6; i++)
-      if (b + i < n) v |= (uint64_t)p[b + i] << (8 * i);
-    const uint32_t r = (uint32_t)((v >> (bp & 7)) & ((1ull << take) - 1));
-    return r << shift;
+    if (pos < lo) fill(((pos - 24) >> 3) * 8);  // keep >= 32 bits above pos available: pos - lo in [24, 31]
+    return (uint32_t)((buf >> (pos - lo)) & ((1ull << nb) - 1));
   }
 };
 

@@ -1,8 +1,3 @@
-python bench.py > gpurun_out/bench_r1q.json 2> gpurun_out/bench_r1q.err; python - <<'PY'
-import json
-b=json.load(open('gpurun_out/bench_r1q.json'))
-print("LZ4 value",b["value"],"ms/step",b["ms_per_step"],"kernels",b["kernels"]); print("e2e",b.get("e2e")); print("cpu",b.get("cpu_baseline")); print("roofline",b["roofline"]["frac"], b["roofline"]["compress_step"]["frac"], b["roofline"]["decompress_step"]["frac"])
-PY
-tail -2 gpurun_out/bench_r1q.err
-python bench.py --codec snappy --steps 2 --warmup 3 --no-cpu 2>&1 | python -c "import json,sys; b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('SNAPPY value',b['value'],'ratio',b['compressed_ratio'],b['kernels']); print(b.get('e2e'))"
-timeout 600 python bench.py --codec zstd --blocks 2000 --steps 1 --warmup 3 --no-cpu --no-e2e 2>&1 | python -c "import json,sys; b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ZSTD value',b['value'],'ratio',b['compressed_ratio'],b['kernels'])"
+python -m pytest tests -m gpu -q -k "lz4 or parity or golden or host" 2>&1 | tail -4
+python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print(b['value'], b['kernels'])"
+ncu --set full --clock-control none -k regex:"lz4_tokens" -c 1 -o gpurun_out/tok_r1r python bench.py --blocks 4000 --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu_tok_r1r.log 2>&1
