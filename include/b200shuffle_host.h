@@ -10,6 +10,7 @@
  *   S3ShuffleHelper            helper/S3ShuffleHelper.scala:44-59 (.index/.checksum), :67-92 (cached readers), :94-103 (algorithms)
  *   S3ShuffleMapOutputWriter   shuffle/S3ShuffleMapOutputWriter.scala:67-83 (getPartitionWriter), :91-118 (commitAllPartitions),
  *                              :168-202 (partition stream), + the GPU "compress on commit" mode of SURVEY.md §3.2 option B
+ *   S3SingleSpillShuffleMapOutputWriter  shuffle/S3SingleSpillShuffleMapOutputWriter.scala:24-64 (+ GPU checksum verification)
  *   S3ShuffleReader            storage/S3ShuffleReader.scala:77-110 (block list -> prefetch -> verify -> decompress),
  *                              storage/S3ShuffleBlockIterator.scala:36-43, storage/S3ShuffleBlockStream.scala:36-40,73-92
  * Only file:// roots are implemented (S3/Hadoop I/O is out of scope).
@@ -65,6 +66,13 @@ int b2sh_writer_close_partition(b2sh_writer* w);
 int b2sh_writer_commit_all_partitions(b2sh_writer* w, const int64_t* checksums_in, int64_t* partition_lengths_out);
 int b2sh_writer_abort(b2sh_writer* w);
 void b2sh_writer_destroy(b2sh_writer* w);
+
+/* ---- single-spill writer (shuffle/S3SingleSpillShuffleMapOutputWriter.scala:24-64): moves an already compressed +
+ * checksummed spill file to the .data object, then writes .checksum and .index.  verify_on_transfer != 0 recomputes the
+ * per-partition checksums over the file on the GPU (b2s_checksum_packed) and fails with B2SH_E_SPARK on a mismatch. ---- */
+int b2sh_single_spill_transfer(b2sh_dispatcher* d, int32_t shuffle_id, int64_t map_id, const char* spill_file,
+                               const int64_t* partition_lengths, const int64_t* checksums, uint32_t num_partitions,
+                               int verify_on_transfer);
 
 /* ---- reader: blocks [start_partition, end_partition) of the given maps ---- */
 typedef struct b2sh_reader b2sh_reader;

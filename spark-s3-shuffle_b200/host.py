@@ -51,6 +51,7 @@ PROTOTYPES = [
     ("b2sh_writer_commit_all_partitions", C.c_int, [_vp, _vp, _vp]),
     ("b2sh_writer_abort", C.c_int, [_vp]),
     ("b2sh_writer_destroy", None, [_vp]),
+    ("b2sh_single_spill_transfer", C.c_int, [_vp, _i32, _i64, C.c_char_p, _vp, _vp, _u32, C.c_int]),
     ("b2sh_reader_create", C.c_int, [_vp, _i32, _vp, _u32, _i32, _i32, C.c_int, C.POINTER(_vp)]),
     ("b2sh_reader_read", C.c_int, [_vp, C.POINTER(_u32)]),
     ("b2sh_reader_block", C.c_int,
@@ -180,6 +181,20 @@ class S3ShuffleMapOutputWriter:
         if self._h:
             load().b2sh_writer_destroy(self._h)
             self._h = None
+
+
+class S3SingleSpillShuffleMapOutputWriter:
+    """shuffle/S3SingleSpillShuffleMapOutputWriter.scala"""
+
+    def __init__(self, dispatcher, shuffleId, mapId):
+        self._d, self.shuffleId, self.mapId = dispatcher, shuffleId, mapId
+
+    def transferMapSpillFile(self, mapSpillFile, partitionLengths, checksums, verifyOnTransfer=False):
+        pl = np.ascontiguousarray(partitionLengths, dtype=np.int64)
+        ck = np.ascontiguousarray(checksums, dtype=np.int64)
+        assert pl.size == ck.size
+        _check(load().b2sh_single_spill_transfer(self._d._h, self.shuffleId, self.mapId, str(mapSpillFile).encode(),
+                                                 pl.ctypes.data, ck.ctypes.data, pl.size, int(verifyOnTransfer)))
 
 
 class S3ShuffleReader:

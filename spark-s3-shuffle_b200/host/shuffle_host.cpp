@@ -403,6 +403,70 @@ class S3ShuffleMapOutputWriter {
   PinnedArena buf_, out_;
 };
 
+// ---- S3SingleSpillShuffleMapOutputWriter (shuffle/S3SingleSpillShuffleMapOutputWriter.scala:24-64) ------------------
+// UnsafeShuffleWriter's single-spill fast path: the spill file already holds the compressed, checksummed partition
+// streams back to back; it is moved (local root: rename, copy when that fails across devices) to the .data object,
+// then .checksum and .index are written — in that order, as the reference does.  SURVEY.md §8(f)-3: with
+// verifyOnTransfer the per-partition checksums are recomputed over the file's bytes by the GPU (one packed batch) and
+// compared with the ones handed in, which is the "checksum-on-the-fly" the copy loop at :54-58 has room for.
+class S3SingleSpillShuffleMapOutputWriter {
+ public:
+  S3SingleSpillShuffleMapOutputWriter(S3ShuffleDispatcher& d, int32_t shuffleId, int64_t mapId)
+      : d_(d), shuffleId_(shuffleId), mapId_(mapId) {}
+
+  void transferMapSpillFile(const std::string& spillFile, const std::vector<int64_t>& partitionLengths,
+                            const std::vector<int64_t>& checksums, bool verifyOnTransfer) {
+    std::string path = d_.getPath(BlockId{BlockId::Data, shuffleId_, mapId_, 0, 0});
+    mkdirs(path.substr(0, path.rfind('/')));
+    if (verifyOnTransfer && d_.checksumEnabled) {
+      const uint32_t alg = S3ShuffleHelper::createChecksumAlgorithm(d_.checksumAlgorithm);
+      std::ifstream f(spillFile, std::ios::binary | std::ios::ate);
+      if (!f) throw IOException("File does not exist: " + spillFile);
+      const uint64_t len = (uint64_t)f.tellg();
+      int64_t sum = 0;
+      for (int64_t v : partitionLengths) sum += v;
+      if ((int64_t)len != sum)
+        throw RuntimeException("S3SingleSpillShuffleMapOutputWriter: Unexpected spill length " + std::to_string(len) +
+                               ", expected: " + std::to_string(sum) + ".");
+      ensure_codec_runtime();
+      PinnedArena buf;
+      buf.resize(len ? len : 1);
+      f.seekg(0);
+      f.read((char*)buf.data(), (std::streamsize)len);
+      const uint32_t n = (uint32_t)partitionLengths.size();
+      std::vector<uint64_t> off(n), ln(n), got(n);
+      uint64_t o = 0;
+      for (uint32_t i = 0; i < n; i++) {
+        off[i] = o;
+        ln[i] = (uint64_t)partitionLengths[i];
+        o += ln[i];
+      }
+      int rc = b2s_checksum_packed(alg, n, buf.data(), off.data(), ln.data(), got.data());
+      if (rc != 0) throw CodecException(std::string("b2s_checksum_packed: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+      for (uint32_t i = 0; i < n; i++)
+        if ((int64_t)got[i] != checksums[i])
+          throw SparkException("Invalid checksum detected for " +
+                               BlockId{BlockId::Shuffle, shuffleId_, mapId_, (int32_t)i, 0}.name());
+    }
+    if (rename(spillFile.c_str(), path.c_str()) != 0) {  // Files.move; falls back to a copy across file systems
+      std::ifstream in(spillFile, std::ios::binary);
+      if (!in) throw IOException("File does not exist: " + spillFile);
+      std::ofstream out(path, std::ios::binary | std::ios::trunc);
+      if (!out) throw IOException("cannot create " + path);
+      out << in.rdbuf();
+      in.close();
+      unlink(spillFile.c_str());
+    }
+    if (d_.checksumEnabled) S3ShuffleHelper::writeChecksum(d_, shuffleId_, mapId_, checksums);  // :60-62
+    S3ShuffleHelper::writePartitionLengths(d_, shuffleId_, mapId_, partitionLengths);             // :63
+  }
+
+ private:
+  S3ShuffleDispatcher& d_;
+  int32_t shuffleId_;
+  int64_t mapId_;
+};
+
 // ---- S3ShuffleReader (storage/S3ShuffleReader.scala + block iterator/stream + checksum validation) ---------
 class S3ShuffleReader {
  public:
@@ -596,6 +660,18 @@ int b2sh_writer_commit_all_partitions(b2sh_writer* w, const int64_t* checksums_i
 }
 int b2sh_writer_abort(b2sh_writer* w) { return guarded([&] { w->w->abort(); }); }
 void b2sh_writer_destroy(b2sh_writer* w) { delete w; }
+
+int b2sh_single_spill_transfer(b2sh_dispatcher* d, int32_t shuffle_id, int64_t map_id, const char* spill_file,
+                               const int64_t* partition_lengths, const int64_t* checksums, uint32_t num_partitions,
+                               int verify_on_transfer) {
+  return guarded([&] {
+    S3SingleSpillShuffleMapOutputWriter w(*d->d, shuffle_id, map_id);
+    std::vector<int64_t> l(partition_lengths, partition_lengths + num_partitions);
+    std::vector<int64_t> c(num_partitions, 0);
+    if (checksums) c.assign(checksums, checksums + num_partitions);
+    w.transferMapSpillFile(spill_file ? spill_file : "", l, c, verify_on_transfer != 0);
+  });
+}
 
 int b2sh_reader_create(b2sh_dispatcher* d, int32_t shuffle_id, const int64_t* map_ids, uint32_t n_maps, int32_t start_partition,
                        int32_t end_partition, int do_batch_fetch, b2sh_reader** out) {

@@ -196,3 +196,23 @@ def test_empty_partitions_and_maps(tmp_path):
         kk, vv, nbytes, blocks = shuffle_read(d, 0, 2, r, r + 1)
         assert len(blocks) == (1 if r == 4 else 0)  # filterNot(maxBytes == 0), storage/S3ShuffleReader.scala:91
     d.close()
+
+
+def test_single_spill_transfer_verifies_checksums_on_the_gpu(tmp_path, oracle):
+    """the single-spill path with checksum-on-the-fly — per-partition checksums recomputed by the GPU
+    over the spill file before it becomes the .data object."""
+    d = host.S3ShuffleDispatcher(conf_for(tmp_path, **{"spark.shuffle.checksum.algorithm": "ADLER32"}))
+    parts = [oracle.lz4block_compress(encode_pairs(np.arange(5000) % (r + 2), np.arange(5000)), 32768) for r in range(4)]
+    lens = [len(p) for p in parts]
+    cks = [oracle.adler32(p) for p in parts]
+    spill = tmp_path / "spill.bin"
+    spill.write_bytes(b"".join(parts))
+    host.S3SingleSpillShuffleMapOutputWriter(d, 0, 0).transferMapSpillFile(spill, lens, cks, verifyOnTransfer=True)
+    k, v, _, blocks = shuffle_read(d, 0, 1, 0, 4)
+    assert len(blocks) == 4 and np.array_equal(np.sort(v), np.sort(np.tile(np.arange(5000), 4)))
+    spill.write_bytes(b"".join(parts))
+    bad = list(cks)
+    bad[2] ^= 1
+    with pytest.raises(host.SparkException, match=r"Invalid checksum detected for shuffle_0_1_2$"):
+        host.S3SingleSpillShuffleMapOutputWriter(d, 0, 1).transferMapSpillFile(spill, lens, bad, verifyOnTransfer=True)
+    d.close()

@@ -171,3 +171,22 @@ def test_gpu_mode_fails_loudly_without_a_device(tmp_path):
         w.commitAllPartitions()
     w.close()
     d.close()
+
+
+def test_single_spill_transfer_moves_file_and_writes_metadata(tmp_path, oracle):
+    """shuffle/S3SingleSpillShuffleMapOutputWriter.scala:24-64 — the spill file (already compressed + checksummed by
+    Spark's UnsafeShuffleWriter, played by the oracle) becomes the .data object; .checksum and .index follow."""
+    d = host.S3ShuffleDispatcher(new_conf(tmp_path, **{"spark.shuffle.checksum.algorithm": "CRC32"}))
+    parts = [oracle.lz4block_compress(bytes([65 + r]) * (1000 * (r + 1)), 32768) for r in range(3)] + [b""]
+    spill = tmp_path / "spill.bin"
+    spill.write_bytes(b"".join(parts))
+    lens = [len(p) for p in parts]
+    cks = [oracle.crc32(p) for p in parts]
+    host.S3SingleSpillShuffleMapOutputWriter(d, 4, 9).transferMapSpillFile(spill, lens, cks)
+    assert not spill.exists()
+    assert open(d.getPath("data", 4, 9), "rb").read() == b"".join(parts)
+    assert open(d.getPath("index", 4, 9), "rb").read() == oracle.index_bytes(lens)
+    assert open(d.getPath("checksum", 4, 9), "rb").read() == oracle.be64_bytes(cks)
+    got = oracle_read_partition(oracle, d, 4, [9], 1, "CRC32")
+    assert got[0][1] == b"B" * 2000
+    d.close()
