@@ -291,22 +291,20 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
   bool fail = false;
   const int mflimit = n - kMFLimit;
   if (n >= kMFLimit + 1) {  // shorter blocks hold no match; the match kernel skipped them (nothing was written to ml[])
-    // 8 positions (one 16-byte load, the next one already in flight) per trip; a match is >= 4 long, so at most two
-    // sequences start in a group: the body is two copies of the same straight-line "take" code, 32-bit arithmetic only
+    // 8 positions (one 16-byte load) per group; a match is >= 4 long, so at most two sequences start in a group: the
+    // body is two copies of the same straight-line "take" code, 32-bit arithmetic only.  Each lane streams through its
+    // own block, so every load is a trip to L2/DRAM (no L1 to speak of while the match kernel of the next chunk holds
+    // the SM's shared memory): a ring of four groups is kept in flight in registers, i.e. every load is issued four
+    // trips (~800 cycles of work) before its use.
     const uint4* __restrict__ mlv = reinterpret_cast<const uint4*>(mlw);
     const int groups = (mflimit >> 3) + 1;
-    uint4 nxt = __ldcs(mlv);
-    for (int g = 0; g < groups; g++) {
-      const uint4 cur = nxt;
-      nxt = __ldcs(mlv + (g + 1 < groups ? g + 1 : g));
-      // each lane streams through its own block, so a miss costs a full DRAM round trip (~2000 cycles) against
-      // ~150 cycles of work per group: pull the sector needed 8 sectors (16 groups) from now into L1 already
-      if ((g & 1) == 0 && g + 16 < groups) asm volatile("prefetch.global.L1 [%0];" ::"l"(mlv + g + 16));
+    auto ld = [&](int g) { return __ldcs(mlv + (g < groups ? g : groups - 1)); };
+    auto body = [&](const uint4 cur, int g) {
       const int base = 8 * g;
-      if (p >= base + 8) continue;  // a match taken earlier covers the whole group (uniform-ish, cheap)
-      unsigned nz = (cur.x & 0xffffu ? 1u : 0u) | (cur.x >> 16 ? 2u : 0u) | (cur.y & 0xffffu ? 4u : 0u) |
-                    (cur.y >> 16 ? 8u : 0u) | (cur.z & 0xffffu ? 16u : 0u) | (cur.z >> 16 ? 32u : 0u) |
-                    (cur.w & 0xffffu ? 64u : 0u) | (cur.w >> 16 ? 128u : 0u);
+      if (fail || p >= base + 8) return;  // a match taken earlier covers the whole group
+      const unsigned nz = (cur.x & 0xffffu ? 1u : 0u) | (cur.x >> 16 ? 2u : 0u) | (cur.y & 0xffffu ? 4u : 0u) |
+                          (cur.y >> 16 ? 8u : 0u) | (cur.z & 0xffffu ? 16u : 0u) | (cur.z >> 16 ? 32u : 0u) |
+                          (cur.w & 0xffffu ? 64u : 0u) | (cur.w >> 16 ? 128u : 0u);
 #pragma unroll
       for (int t = 0; t < 2; t++) {
         const int rel = p - base;  // >= 0
@@ -352,7 +350,29 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
           p = base + 8;
         }
       }
-      if (fail) break;
+    };
+    uint4 r0 = ld(0), r1 = ld(1), r2 = ld(2), r3 = ld(3);
+    for (int g = 0; g < groups && !fail; g += 4) {
+      {
+        const uint4 c = r0;
+        r0 = ld(g + 4);
+        body(c, g);
+      }
+      if (g + 1 < groups) {
+        const uint4 c = r1;
+        r1 = ld(g + 5);
+        body(c, g + 1);
+      }
+      if (g + 2 < groups) {
+        const uint4 c = r2;
+        r2 = ld(g + 6);
+        body(c, g + 2);
+      }
+      if (g + 3 < groups) {
+        const uint4 c = r3;
+        r3 = ld(g + 7);
+        body(c, g + 3);
+      }
     }
   }
   if (ZSTD) {  // trailing literals as a final ml == 0 record; sizes are decided by the entropy stage
@@ -471,8 +491,23 @@ __global__ void __launch_bounds__(kEmitThreads) lz4_emit_kernel(
         uint8_t* q = out + op;
         *q++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mlc < 15 ? mlc : 15));
         if (lit >= 15) *q++ = (uint8_t)(lit - 15);
-        const uint8_t* ls = s + anchor;
-        for (int j = 0; j < lit; j++) q[j] = __ldg(ls + j);
+        // literals (<= 16 bytes): aligned word loads + funnel shifts into four registers, then predicated byte stores
+        // — a per-byte load loop would be one L2 round trip per byte whenever L1 is not there to absorb it
+        if (lit) {
+          const uintptr_t la = reinterpret_cast<uintptr_t>(s + anchor);
+          const uint32_t* lw = reinterpret_cast<const uint32_t*>(la & ~uintptr_t(3));
+          const unsigned lsh = (la & 3u) * 8u;
+          const int need = (int)(la & 3u) + lit;  // bytes from the first aligned word on
+          const uint32_t w0 = __ldg(lw), w1 = need > 4 ? __ldg(lw + 1) : 0u, w2 = need > 8 ? __ldg(lw + 2) : 0u,
+                         w3 = need > 12 ? __ldg(lw + 3) : 0u, w4 = need > 16 ? __ldg(lw + 4) : 0u;
+          const uint32_t r0 = __funnelshift_r(w0, w1, lsh), r1 = __funnelshift_r(w1, w2, lsh),
+                         r2 = __funnelshift_r(w2, w3, lsh), r3 = __funnelshift_r(w3, w4, lsh);
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const uint32_t r = j < 4 ? r0 : j < 8 ? r1 : j < 12 ? r2 : r3;
+            if (j < lit) q[j] = (uint8_t)(r >> (8 * (j & 3)));
+          }
+        }
         q += lit;
         q[0] = (uint8_t)off;
         q[1] = (uint8_t)(off >> 8);

@@ -15,47 +15,57 @@ constexpr uint32_t XP1 = 2654435761u, XP2 = 2246822519u, XP3 = 3266489917u, XP4 
 
 __device__ __forceinline__ uint32_t xxh_round(uint32_t acc, uint32_t x) { return rotl32(acc + x * XP2, 13) * XP1; }
 
-// p may have any alignment; reads only aligned words that contain bytes of [p, p+n)
+// 4 words at word offset K (0..3) and bit shift sh (0, 8, 16, 24) inside the 8 words lo|hi
+template <int K>
+__device__ __forceinline__ void pick4(const uint4& lo, const uint4& hi, unsigned sh, uint32_t& a, uint32_t& b,
+                                      uint32_t& c, uint32_t& d) {
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  a = __funnelshift_r(w[K], w[K + 1], sh);
+  b = __funnelshift_r(w[K + 1], w[K + 2], sh);
+  c = __funnelshift_r(w[K + 2], w[K + 3], sh);
+  d = __funnelshift_r(w[K + 3], w[K + 4], sh);
+}
+
+// the 16-byte stripes of [p, p + 16*stripes) for ANY alignment of p: one aligned 128-bit load per stripe (the previous
+// chunk is carried in registers) + funnel shifts.  One thread per block means every load instruction is 32 wavefronts on
+// the LSU pipe, so the 4 x 32-bit loads per stripe of the first version were the bottleneck (1.6 TB/s), not HBM.
+// Reads only aligned 16-byte chunks that contain bytes of the range.
+template <int K>
+__device__ __forceinline__ void xxh_stripes(const uint4* __restrict__ q, unsigned sh, uint32_t stripes, bool tail_chunk,
+                                            uint32_t& v1, uint32_t& v2, uint32_t& v3, uint32_t& v4) {
+  uint4 lo = __ldg(q);
+#pragma unroll 4
+  for (uint32_t s = 0; s < stripes; s++) {
+    // the chunk after the last stripe holds range bytes only when the range is not 16-byte aligned (K or sh != 0)
+    const uint4 hi = (s + 1 < stripes || tail_chunk) ? __ldg(q + s + 1) : make_uint4(0, 0, 0, 0);
+    uint32_t a, b, c, d;
+    pick4<K>(lo, hi, sh, a, b, c, d);
+    v1 = xxh_round(v1, a);
+    v2 = xxh_round(v2, b);
+    v3 = xxh_round(v3, c);
+    v4 = xxh_round(v4, d);
+    lo = hi;
+  }
+}
+
+// p may have any alignment; reads only aligned chunks/words that contain bytes of [p, p+n)
 __device__ uint32_t xxh32_device(const uint8_t* p, uint32_t n, uint32_t seed) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const unsigned sh = (a & 3u) * 8u;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
   uint32_t h;
   uint32_t i = 0;  // bytes consumed
   if (n >= 16) {
     uint32_t v1 = seed + XP1 + XP2, v2 = seed + XP2, v3 = seed, v4 = seed - XP1;
     const uint32_t stripes = n >> 4;
-    if (sh == 0) {
-      if ((a & 15u) == 0) {
-        const uint4* q = reinterpret_cast<const uint4*>(p);
-#pragma unroll 4
-        for (uint32_t s = 0; s < stripes; s++) {
-          uint4 x = q[s];
-          v1 = xxh_round(v1, x.x);
-          v2 = xxh_round(v2, x.y);
-          v3 = xxh_round(v3, x.z);
-          v4 = xxh_round(v4, x.w);
-        }
-      } else {
-#pragma unroll 4
-        for (uint32_t s = 0; s < stripes; s++) {
-          v1 = xxh_round(v1, w[4 * s]);
-          v2 = xxh_round(v2, w[4 * s + 1]);
-          v3 = xxh_round(v3, w[4 * s + 2]);
-          v4 = xxh_round(v4, w[4 * s + 3]);
-        }
-      }
-    } else {
-      uint32_t carry = w[0];
-#pragma unroll 2
-      for (uint32_t s = 0; s < stripes; s++) {
-        uint32_t b = w[4 * s + 1], c = w[4 * s + 2], d = w[4 * s + 3], e = w[4 * s + 4];
-        v1 = xxh_round(v1, __funnelshift_r(carry, b, sh));
-        v2 = xxh_round(v2, __funnelshift_r(b, c, sh));
-        v3 = xxh_round(v3, __funnelshift_r(c, d, sh));
-        v4 = xxh_round(v4, __funnelshift_r(d, e, sh));
-        carry = e;
-      }
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned sh = (a & 3u) * 8u;
+    const int k = (int)((a >> 2) & 3u);
+    const uint4* q = reinterpret_cast<const uint4*>(a & ~uintptr_t(15));
+    // bytes of the range inside the chunk that follows the last full stripe's chunk?
+    const bool tail_chunk = (a & 15u) != 0;
+    switch (k) {
+      case 0: xxh_stripes<0>(q, sh, stripes, tail_chunk, v1, v2, v3, v4); break;
+      case 1: xxh_stripes<1>(q, sh, stripes, tail_chunk, v1, v2, v3, v4); break;
+      case 2: xxh_stripes<2>(q, sh, stripes, tail_chunk, v1, v2, v3, v4); break;
+      default: xxh_stripes<3>(q, sh, stripes, tail_chunk, v1, v2, v3, v4); break;
     }
     i = stripes << 4;
     h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
