@@ -49,7 +49,8 @@ constexpr uint32_t kChunkStreams = 1u << 18;
 constexpr uint32_t kXxhSeed = 0x9747b28cu;
 uint32_t g_lz4_chunk_blocks = 32768;  // codec blocks per match/parse/emit (or tokens/copy) pass: bounds the workspace; B2S_LZ4_CHUNK_BLOCKS
 uint32_t g_lz4d_chunk_blocks = 65536;  // decode side: the token walk is latency bound, more blocks per launch = more loads in flight; B2S_LZ4D_CHUNK_BLOCKS
-int g_lz4d_legacy = 0;  // B2S_LZ4D_LEGACY=1: single-kernel tile decoder for every block size (A/B comparisons)
+int g_lz4d_legacy = 0;
+int g_trace = 0;  // B2S_TRACE=1: per-chunk timeline of the compress pipeline on stderr  // B2S_LZ4D_LEGACY=1: single-kernel tile decoder for every block size (A/B comparisons)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -130,6 +131,7 @@ struct Slot {
   PinBuf hmeta;
   // per-launch event pairs around the dominant kernel of a call (grow-only pool; `used` pairs are valid)
   std::vector<cudaEvent_t> ev_dom;
+  std::vector<cudaEvent_t> trace;  // B2S_TRACE=1: (match0, match1, tail0, tail1) per compress chunk, printed by add_timing
   size_t dom_used = 0;
   int dom_pair(cudaEvent_t* a, cudaEvent_t* b) {
     if (dom_used * 2 + 2 > ev_dom.size()) {
@@ -327,8 +329,17 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
                      e0, e1);
     CU(cudaEventRecord(S.ev_match[par], S.st2));
     CU(cudaStreamWaitEvent(st, S.ev_match[par], 0));
+    cudaEvent_t t0 = nullptr, t1 = nullptr, tp = nullptr;
+    if (g_trace && S.trace.size() < 4096) {
+      cudaEventCreate(&t0);
+      cudaEventCreate(&t1);
+      cudaEventCreate(&tp);
+      S.trace.push_back(e0); S.trace.push_back(e1); S.trace.push_back(t0); S.trace.push_back(t1); S.trace.push_back(tp);
+      CU(cudaEventRecord(t0, st));
+    }
     launch_lz4_parse_emit(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, codec, ws, M.nseq, M.csize, M.hash,
-                          M.sizes, M.total, M.ws, d_dst, dst_cap, st, launches);
+                          M.sizes, M.total, M.ws, d_dst, dst_cap, st, launches, tp);
+    if (t1) CU(cudaEventRecord(t1, st));
     CU(cudaEventRecord(S.ev_free[par], st));
   }
   CU(cudaEventRecord(S.ev_t1, st));
@@ -563,6 +574,18 @@ void add_timing(Slot& S, bool copies) {
     t_timing.dominant_ms += ms_between(S.ev_dom[2 * k], S.ev_dom[2 * k + 1]);
     t_timing.dominant_launches++;
   }
+  if (g_trace && !S.trace.empty()) {
+    cudaEvent_t base = S.trace[0];
+    for (size_t k = 0; k + 4 < S.trace.size(); k += 5) {
+      fprintf(stderr, "chunk %2zu: match %7.3f..%7.3f  parse %7.3f..%7.3f  scan+emit ..%7.3f ms\n", k / 5,
+              ms_between(base, S.trace[k]), ms_between(base, S.trace[k + 1]), ms_between(base, S.trace[k + 2]),
+              ms_between(base, S.trace[k + 4]), ms_between(base, S.trace[k + 3]));
+      cudaEventDestroy(S.trace[k + 2]);
+      cudaEventDestroy(S.trace[k + 3]);
+      cudaEventDestroy(S.trace[k + 4]);
+    }
+    S.trace.clear();
+  }
   S.dom_used = 0;
   if (copies) t_timing.h2d_ms += ms_between(S.ev_h0, S.ev_h1);  // d2h is added once the payload copy has run
 }
@@ -651,6 +674,7 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
   g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
   g_lz4_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4_CHUNK_BLOCKS", (int)g_lz4_chunk_blocks));
   g_lz4d_legacy = env_int("B2S_LZ4D_LEGACY", 0);
+  g_trace = env_int("B2S_TRACE", 0);
   g_lz4d_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4D_CHUNK_BLOCKS", (int)g_lz4d_chunk_blocks));
   g_host_chunk_bytes = (uint64_t)std::max(1, env_int("B2S_HOST_CHUNK_MB", (int)(g_host_chunk_bytes >> 20))) << 20;
   Context* C = new Context();

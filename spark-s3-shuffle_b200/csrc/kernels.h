@@ -59,7 +59,8 @@ void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, c
                            const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
                            uint32_t block_size, uint32_t codec, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,
                            const uint32_t* d_hash, uint64_t* d_sizes, uint64_t* d_running_total, uint64_t* d_scan_ws,
-                           uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches);
+                           uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches,
+                           cudaEvent_t ev_parsed = nullptr);
 // per stream: dst_off/dst_len, end mark, B2S_E_DST_TOO_SMALL (d_scan = packed block offsets, d_scan_total = their sum)
 void launch_lz4block_stream_meta(const uint32_t* d_blk_base, uint32_t n_streams, uint32_t n_blocks, uint32_t block_size,
                                  const uint64_t* d_scan, const uint64_t* d_scan_total, uint8_t* dst_base,

@@ -614,7 +614,8 @@ void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, c
                            const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
                            uint32_t block_size, uint32_t codec, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,
                            const uint32_t* d_hash, uint64_t* d_sizes, uint64_t* d_running_total, uint64_t* d_scan_ws,
-                           uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches) {
+                           uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches,
+                           cudaEvent_t ev_parsed) {
   if (!m) return;
   const Lz4Ws w = carve_ws(d_ws, m, block_size);
   if (codec == B2S_CODEC_ZSTD) {
@@ -640,7 +641,8 @@ void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, c
     return;
   }
   lz4_parse_kernel<0><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
-                                                        w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+                                                    w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+  if (ev_parsed) cudaEventRecord(ev_parsed, st);  // B2S_TRACE timeline
   // packed offsets of this chunk's blocks, chained onto the running total of the chunks before it
   launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);
   lz4_emit_kernel<<<(m + kEmitThreads / 32 - 1) / (kEmitThreads / 32), kEmitThreads, 0, st>>>(
