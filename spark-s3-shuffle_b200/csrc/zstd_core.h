@@ -19,6 +19,22 @@
 #define B2S_HD
 #endif
 
+// Cooperative execution.  On the device the decoder runs with ALL 32 lanes of a warp executing the same control flow on
+// the same data (the serial parts are simply computed redundantly, which costs a warp no more than one lane would),
+// so that the byte-copy loops can be split across the lanes and the four Huffman streams of a literals section across
+// four lanes.  zstd.cu defines B2S_ZSTD_WARP before including this header; everywhere else one "lane" does everything.
+#if defined(B2S_ZSTD_WARP) && defined(__CUDA_ARCH__)
+#define B2S_LANE ((int)(threadIdx.x & 31))
+#define B2S_NLANES 32
+#define B2S_SYNC() __syncwarp()
+#define B2S_ALL(pred) (__all_sync(0xffffffffu, (pred)))
+#else
+#define B2S_LANE 0
+#define B2S_NLANES 1
+#define B2S_SYNC() ((void)0)
+#define B2S_ALL(pred) (pred)
+#endif
+
 namespace b2s {
 namespace zstd {
 
@@ -32,13 +48,13 @@ struct FseEntry {
   uint16_t base;
 };
 
-// per-frame decoder state; lives in global memory on the device (one per frame in flight)
+// per-stream decoder state: ~11 KB of tables (shared memory on the device) + a pointer to the literals buffer
 struct Workspace {
   FseEntry ll[512], of[256], ml[512];
   FseEntry wt[64];        // Huffman weights (FSE, accuracy <= 6)
   uint16_t huf[2048];     // Huffman decoding table: symbol | nbits << 8, 2^maxbits entries (maxbits <= 11)
   uint8_t weights[256];
-  uint8_t lit[kBlockMax + 64];
+  uint8_t* lit;           // kBlockMax + 64 bytes (global memory on the device; the tables above sit in shared memory)
   int16_t norm[64];
   uint16_t next[64];
   int ll_log, of_log, ml_log, huf_bits;
@@ -284,21 +300,26 @@ B2S_HD inline bool huf_decode_stream(const Workspace* w, const uint8_t* src, uin
 }
 
 // ---- sequences ---------------------------------------------------------------------------------------------------
+// Code -> (baseline, extra bits), RFC 8878 tables 3.1.1.3.2.1.1, in closed form: a function-local lookup table would be
+// rebuilt on the (local-memory) stack for every sequence on the device.
 B2S_HD inline void ll_code(int c, uint32_t* base, int* bits) {
-  const uint32_t b[36] = {0,  1,  2,  3,  4,  5,  6,  7,  8,   9,   10,  11,   12,   13,   14,   15,    16,    18,
-                          20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
-  const uint8_t e[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-  *base = b[c];
-  *bits = e[c];
+  if (c < 16) { *base = (uint32_t)c; *bits = 0; }
+  else if (c < 20) { *base = 16u + 2u * (uint32_t)(c - 16); *bits = 1; }
+  else if (c < 22) { *base = 24u + 4u * (uint32_t)(c - 20); *bits = 2; }
+  else if (c < 24) { *base = 32u + 8u * (uint32_t)(c - 22); *bits = 3; }
+  else if (c == 24) { *base = 48u; *bits = 4; }
+  else if (c == 25) { *base = 64u; *bits = 6; }
+  else { *base = 1u << (c - 19); *bits = c - 19; }
 }
 B2S_HD inline void ml_code(int c, uint32_t* base, int* bits) {
-  const uint32_t b[53] = {3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20,
-                          21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41,
-                          43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
-  const uint8_t e[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-                         0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-  *base = b[c];
-  *bits = e[c];
+  if (c < 32) { *base = (uint32_t)c + 3u; *bits = 0; }
+  else if (c < 36) { *base = 35u + 2u * (uint32_t)(c - 32); *bits = 1; }
+  else if (c < 38) { *base = 43u + 4u * (uint32_t)(c - 36); *bits = 2; }
+  else if (c < 40) { *base = 51u + 8u * (uint32_t)(c - 38); *bits = 3; }
+  else if (c < 42) { *base = 67u + 16u * (uint32_t)(c - 40); *bits = 4; }
+  else if (c == 42) { *base = 99u; *bits = 5; }
+  else if (c == 43) { *base = 131u; *bits = 7; }
+  else { *base = (1u << (c - 36)) + 3u; *bits = c - 36; }
 }
 
 // kind: 0 = literal lengths, 1 = offsets, 2 = match lengths
@@ -413,7 +434,10 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
   } else if (ltype == 1) {
     if (ip + 1 > n) return kErrCorrupt;
     if (!size_only)
-      for (uint64_t i = 0; i < regen; i++) w->lit[i] = src[ip];
+    {
+      for (uint64_t i = B2S_LANE; i < regen; i += B2S_NLANES) w->lit[i] = src[ip];
+      B2S_SYNC();
+    }
     lit = w->lit;
     ip += 1;
   } else {
@@ -431,7 +455,10 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
     }
     if (!size_only) {
       if (streams == 1) {
-        if (!huf_decode_stream(w, ls, ln, w->lit, regen)) return kErrCorrupt;
+        bool ok1 = true;
+        if (B2S_LANE == 0) ok1 = huf_decode_stream(w, ls, ln, w->lit, regen);
+        B2S_SYNC();
+        if (!B2S_ALL(ok1)) return kErrCorrupt;
       } else {
         if (ln < 6) return kErrCorrupt;
         const uint64_t s1 = ls[0] | (ls[1] << 8), s2 = ls[2] | (ls[3] << 8), s3 = ls[4] | (ls[5] << 8);
@@ -440,10 +467,23 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
         const uint64_t q = (regen + 3) / 4;
         if (3 * q > regen) return kErrCorrupt;
         const uint8_t* a = ls + 6;
+#if defined(B2S_ZSTD_WARP) && defined(__CUDA_ARCH__)
+        {  // one lane per stream; every lane needs the verdict
+          bool ok = true;
+          const int l = B2S_LANE;
+          if (l == 0) ok = huf_decode_stream(w, a, s1, w->lit, q);
+          else if (l == 1) ok = huf_decode_stream(w, a + s1, s2, w->lit + q, q);
+          else if (l == 2) ok = huf_decode_stream(w, a + s1 + s2, s3, w->lit + 2 * q, q);
+          else if (l == 3) ok = huf_decode_stream(w, a + s1 + s2 + s3, s4, w->lit + 3 * q, regen - 3 * q);
+          B2S_SYNC();
+          if (!B2S_ALL(ok)) return kErrCorrupt;
+        }
+#else
         if (!huf_decode_stream(w, a, s1, w->lit, q)) return kErrCorrupt;
         if (!huf_decode_stream(w, a + s1, s2, w->lit + q, q)) return kErrCorrupt;
         if (!huf_decode_stream(w, a + s1 + s2, s3, w->lit + 2 * q, q)) return kErrCorrupt;
         if (!huf_decode_stream(w, a + s1 + s2 + s3, s4, w->lit + 3 * q, regen - 3 * q)) return kErrCorrupt;
+#endif
       }
     }
     lit = w->lit;
@@ -515,10 +555,18 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
         const uint64_t o = op + produced;
         if (o + llen + mlen > cap) return kErrDstTooSmall;
         if ((uint64_t)offset > o + llen) return kErrCorrupt;  // reaches before the start of the frame
-        for (uint32_t k = 0; k < llen; k++) out[o + k] = lit[lpos + k];
+        for (uint32_t k = B2S_LANE; k < llen; k += B2S_NLANES) out[o + k] = lit[lpos + k];
+        B2S_SYNC();  // the match may start inside these literals
         uint8_t* d = out + o + llen;
         const uint8_t* s = d - offset;
-        for (uint32_t k = 0; k < mlen; k++) d[k] = s[k];
+        if (B2S_NLANES == 1) {
+          for (uint32_t k = 0; k < mlen; k++) d[k] = s[k];
+        } else if (offset >= mlen) {
+          for (uint32_t k = B2S_LANE; k < mlen; k += B2S_NLANES) d[k] = s[k];
+        } else {  // overlapping match: every byte comes from the already complete window [d - offset, d)
+          for (uint32_t k = B2S_LANE; k < mlen; k += B2S_NLANES) d[k] = s[k % offset];
+        }
+        B2S_SYNC();
       }
       lpos += llen;
       produced += (uint64_t)llen + mlen;
@@ -536,7 +584,8 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
   if (!size_only) {
     const uint64_t o = op + produced;
     if (o + tail > cap) return kErrDstTooSmall;
-    for (uint64_t k = 0; k < tail; k++) out[o + k] = lit[lpos + k];
+    for (uint64_t k = B2S_LANE; k < tail; k += B2S_NLANES) out[o + k] = lit[lpos + k];
+    B2S_SYNC();
   }
   return (int64_t)(produced + tail);
 }
@@ -597,7 +646,8 @@ B2S_HD inline int64_t decode_stream(Workspace* w, const uint8_t* src, uint64_t n
         if (bsize > n - ip) return kErrCorrupt;
         if (!size_only) {
           if (op + bsize > room) return kErrDstTooSmall;
-          for (uint32_t k = 0; k < bsize; k++) out[op + k] = src[ip + k];
+          for (uint32_t k = B2S_LANE; k < bsize; k += B2S_NLANES) out[op + k] = src[ip + k];
+          B2S_SYNC();
         }
         ip += bsize;
         op += bsize;
@@ -605,7 +655,8 @@ B2S_HD inline int64_t decode_stream(Workspace* w, const uint8_t* src, uint64_t n
         if (ip >= n) return kErrCorrupt;
         if (!size_only) {
           if (op + bsize > room) return kErrDstTooSmall;
-          for (uint32_t k = 0; k < bsize; k++) out[op + k] = src[ip];
+          for (uint32_t k = B2S_LANE; k < bsize; k += B2S_NLANES) out[op + k] = src[ip];
+          B2S_SYNC();
         }
         ip += 1;
         op += bsize;

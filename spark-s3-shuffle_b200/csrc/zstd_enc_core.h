@@ -114,12 +114,19 @@ B2S_HD inline void ll_encode(uint32_t ll, int* code, int* nbits, uint32_t* extra
   } else {
     c = highbit(ll) + 19;
   }
-  const uint32_t base[36] = {0,  1,  2,  3,  4,  5,  6,  7,  8,   9,   10,  11,   12,   13,   14,   15,    16,    18,
-                             20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
-  const uint8_t bits[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+  // baseline / extra bits in closed form (RFC 8878 table of literal-length codes): no per-call lookup table
+  uint32_t base;
+  int nb;
+  if (c < 16) { base = (uint32_t)c; nb = 0; }
+  else if (c < 20) { base = 16u + 2u * (uint32_t)(c - 16); nb = 1; }
+  else if (c < 22) { base = 24u + 4u * (uint32_t)(c - 20); nb = 2; }
+  else if (c < 24) { base = 32u + 8u * (uint32_t)(c - 22); nb = 3; }
+  else if (c == 24) { base = 48u; nb = 4; }
+  else if (c == 25) { base = 64u; nb = 6; }
+  else { base = 1u << (c - 19); nb = c - 19; }
   *code = c;
-  *nbits = bits[c];
-  *extra = ll - base[c];
+  *nbits = nb;
+  *extra = ll - base;
 }
 // match length (>= 3) -> code, extra bits, extra value
 B2S_HD inline void ml_encode(uint32_t ml, int* code, int* nbits, uint32_t* extra) {
@@ -133,14 +140,19 @@ B2S_HD inline void ml_encode(uint32_t ml, int* code, int* nbits, uint32_t* extra
   } else {
     c = highbit(mb) + 36;
   }
-  const uint32_t base[53] = {3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20,
-                             21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41,
-                             43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
-  const uint8_t bits[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-                            0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+  uint32_t base;
+  int nb;
+  if (c < 32) { base = (uint32_t)c + 3u; nb = 0; }
+  else if (c < 36) { base = 35u + 2u * (uint32_t)(c - 32); nb = 1; }
+  else if (c < 38) { base = 43u + 4u * (uint32_t)(c - 36); nb = 2; }
+  else if (c < 40) { base = 51u + 8u * (uint32_t)(c - 38); nb = 3; }
+  else if (c < 42) { base = 67u + 16u * (uint32_t)(c - 40); nb = 4; }
+  else if (c == 42) { base = 99u; nb = 5; }
+  else if (c == 43) { base = 131u; nb = 7; }
+  else { base = (1u << (c - 36)) + 3u; nb = c - 36; }
   *code = c;
-  *nbits = bits[c];
-  *extra = ml - base[c];
+  *nbits = nb;
+  *extra = ml - base;
 }
 
 // ---- forward bit writer (the sequence bitstream is written forwards, sequences in reverse order) ------------------

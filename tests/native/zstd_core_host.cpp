@@ -8,13 +8,17 @@
 extern "C" {
 long long zc_decode(const unsigned char* src, unsigned long long n, unsigned char* dst, unsigned long long cap) {
   b2s::zstd::Workspace* w = (b2s::zstd::Workspace*)malloc(sizeof(b2s::zstd::Workspace));
+  w->lit = (unsigned char*)malloc(b2s::zstd::kBlockMax + 64);
   long long r = b2s::zstd::decode_stream(w, src, n, dst, cap, false);
+  free(w->lit);
   free(w);
   return r;
 }
 long long zc_size(const unsigned char* src, unsigned long long n) {
   b2s::zstd::Workspace* w = (b2s::zstd::Workspace*)malloc(sizeof(b2s::zstd::Workspace));
+  w->lit = (unsigned char*)malloc(b2s::zstd::kBlockMax + 64);
   long long r = b2s::zstd::decode_stream(w, src, n, nullptr, 0, true);
+  free(w->lit);
   free(w);
   return r;
 }

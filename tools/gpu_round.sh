@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -4
-python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print('H12', b['value'], b['compressed_ratio'], b['kernels'])"
-B2S_LZ4_HLOG=11 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print('H11', b['value'], b['compressed_ratio'], b['kernels'])"
+python -m pytest tests/test_gpu_zstd.py -m gpu -q 2>&1 | tail -8
+timeout 600 python bench.py --codec zstd --blocks 2000 --steps 1 --warmup 3 --no-cpu --no-e2e 2>&1 | python -c "import json,sys; b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ZSTD 2000', b['value'],'ratio',b['compressed_ratio'],b['kernels'])"
+timeout 900 python bench.py --codec zstd --steps 1 --warmup 3 --no-cpu --no-e2e 2>&1 | python -c "import json,sys; b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ZSTD 16000', b['value'],'ratio',b['compressed_ratio'],b['kernels'])"
