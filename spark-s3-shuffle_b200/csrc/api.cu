@@ -536,7 +536,14 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
       const int par = (int)(k & 1);
       uint8_t* ws = (uint8_t*)S.scratch.p + nrec_bytes + (size_t)par * ws_bytes;
       if (k >= 2) CU(cudaStreamWaitEvent(S.st2, S.ev_free[par], 0));
+      cudaEvent_t q0 = nullptr, q1 = nullptr;
+      if (g_trace && S.trace.size() < 4096) {
+        cudaEventCreate(&q0);
+        cudaEventCreate(&q1);
+        CU(cudaEventRecord(q0, S.st2));
+      }
       launch_lz4_tokens(J.codec, desc, b0, m, rec_stride, d_src, ws, nrec, J.status, S.st2, launches);
+      if (q1) CU(cudaEventRecord(q1, S.st2));
       CU(cudaEventRecord(S.ev_match[par], S.st2));
       CU(cudaStreamWaitEvent(st, S.ev_match[par], 0));
       cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -544,6 +551,15 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
       CU(cudaEventRecord(e0, st));
       launch_lz4_copy(desc, b0, m, rec_stride, d_src, d_dst, ws, nrec, st, launches);
       CU(cudaEventRecord(e1, st));
+      if (q0) {  // trace rows: (tokens0, tokens1, copy0, copy1, copy1)
+        S.trace.push_back(q0); S.trace.push_back(q1);
+        cudaEvent_t c0 = nullptr, c1 = nullptr, c2 = nullptr;
+        cudaEventCreate(&c0); cudaEventCreate(&c1); cudaEventCreate(&c2);
+        // e0/e1 belong to the dom pool; re-record private copies right here (same stream position as e1)
+        CU(cudaEventRecord(c1, st)); CU(cudaEventRecord(c2, st));
+        S.trace.push_back(e0); S.trace.push_back(c1); S.trace.push_back(c2);
+        cudaEventDestroy(c0);
+      }
       CU(cudaEventRecord(S.ev_free[par], st));
     }
   } else if (J.nb) {
@@ -577,10 +593,10 @@ void add_timing(Slot& S, bool copies) {
   if (g_trace && !S.trace.empty()) {
     cudaEvent_t base = S.trace[0];
     for (size_t k = 0; k + 4 < S.trace.size(); k += 5) {
-      fprintf(stderr, "chunk %2zu: match %7.3f..%7.3f  parse %7.3f..%7.3f  scan+emit ..%7.3f ms\n", k / 5,
+      fprintf(stderr, "chunk %2zu: A(match|tokens) %7.3f..%7.3f  B(parse|copy) %7.3f..%7.3f  end %7.3f ms\n", k / 5,
               ms_between(base, S.trace[k]), ms_between(base, S.trace[k + 1]), ms_between(base, S.trace[k + 2]),
               ms_between(base, S.trace[k + 4]), ms_between(base, S.trace[k + 3]));
-      cudaEventDestroy(S.trace[k + 2]);
+      // (events at k, k+1 [compress] / k+2 [decode] belong to the dominant-kernel pool or are leaked: tracing only)
       cudaEventDestroy(S.trace[k + 3]);
       cudaEventDestroy(S.trace[k + 4]);
     }
