@@ -42,7 +42,7 @@ int fail_cuda(const char* what, cudaError_t e) {
     if (e__ != cudaSuccess) return fail_cuda(#call, e__);  \
   } while (0)
 
-constexpr int NSLOT = 4;
+constexpr int NSLOT = 6;
 uint64_t g_host_chunk_bytes = 256ull << 20;  // host-pointer calls: bytes per pipeline chunk (B2S_HOST_CHUNK_MB).  The thread-per-block
                                               // kernels cost ~2 ms per launch whatever the block count, so chunks must be large enough to amortise them
 constexpr uint32_t kChunkStreams = 1u << 18;

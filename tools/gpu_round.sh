@@ -1,3 +1,2 @@
-compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests -m gpu -q -x -k "not full_size and not many_shuffle and not combineByKey" 2>&1 | tail -8 > gpurun_out/sanitizer_r1s.log; tail -8 gpurun_out/sanitizer_r1s.log
-python -m pytest tests -m gpu -q 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()"
+python bench.py --steps 2 --warmup 3 --no-cpu 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print('NSLOT6', b['value']); print(b['e2e'])"
+B2S_HOST_CHUNK_MB=128 python bench.py --steps 2 --warmup 3 --no-cpu 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print('NSLOT6 chunk128', b['e2e'])"
