@@ -18,6 +18,9 @@
 #else
 #define B2S_HD
 #endif
+#if defined(B2S_ZSTD_WARP) && defined(__CUDACC__)
+#include "lz_batch.cuh"  // lz_execute_matches: the dependency-round executor shared with the LZ4 / Snappy copy kernel
+#endif
 
 // Cooperative execution.  On the device the decoder runs with ALL 32 lanes of a warp executing the same control flow on
 // the same data (the serial parts are simply computed redundantly, which costs a warp no more than one lane would),
@@ -518,6 +521,9 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
     BitsRev br;
     if (ip >= n || !br.init(src + ip, n - ip)) return kErrCorrupt;
     uint32_t sl = br.read(w->ll_log), so = br.read(w->of_log), sm = br.read(w->ml_log);
+#if defined(B2S_ZSTD_WARP) && defined(__CUDA_ARCH__)
+    int my_ll = 0, my_ml = 0, my_off = 0, my_lpos = 0, my_o = 0, nb = 0;
+#endif
     for (uint32_t i = 0; i < nseq; i++) {
       const int oc = w->of[so].sym, mc = w->ml[sm].sym, lc = w->ll[sl].sym;
       if (oc > 31 || mc > 52 || lc > 35) return kErrCorrupt;
@@ -555,18 +561,41 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
         const uint64_t o = op + produced;
         if (o + llen + mlen > cap) return kErrDstTooSmall;
         if ((uint64_t)offset > o + llen) return kErrCorrupt;  // reaches before the start of the frame
-        for (uint32_t k = B2S_LANE; k < llen; k += B2S_NLANES) out[o + k] = lit[lpos + k];
-        B2S_SYNC();  // the match may start inside these literals
+#if defined(B2S_ZSTD_WARP) && defined(__CUDA_ARCH__)
+        // warp build: lane `nb` latches this sequence; 32 of them are then executed together (below)
+        if (B2S_LANE == nb) {
+          my_ll = (int)llen;
+          my_ml = (int)mlen;
+          my_off = (int)offset;
+          my_lpos = (int)lpos;
+          my_o = (int)produced;
+        } else if (B2S_LANE > nb) {  // not latched yet: sit (empty) at the end of what has been decoded
+          my_ll = my_ml = 0;
+          my_o = (int)(produced + llen + mlen);
+        }
+        nb++;
+        if (nb == 32 || i + 1 == nseq) {
+          uint8_t* ob = out + op;  // block base: positions inside the block fit an int, earlier output is final
+          if (my_ll <= 32)
+            for (int k = 0; k < my_ll; k++) ob[my_o + k] = lit[my_lpos + k];
+          unsigned big = __ballot_sync(0xffffffffu, my_ll > 32);
+          while (big) {
+            const int l = __ffs(big) - 1;
+            big &= big - 1;
+            const int n_l = __shfl_sync(0xffffffffu, my_ll, l), o_l = __shfl_sync(0xffffffffu, my_o, l),
+                      p_l = __shfl_sync(0xffffffffu, my_lpos, l);
+            for (int k = B2S_LANE; k < n_l; k += 32) ob[o_l + k] = lit[p_l + k];
+          }
+          __syncwarp();
+          lz_execute_matches(ob, my_o + my_ll, my_ml, my_off, B2S_LANE);
+          nb = 0;
+        }
+#else
+        for (uint32_t k = 0; k < llen; k++) out[o + k] = lit[lpos + k];
         uint8_t* d = out + o + llen;
         const uint8_t* s = d - offset;
-        if (B2S_NLANES == 1) {
-          for (uint32_t k = 0; k < mlen; k++) d[k] = s[k];
-        } else if (offset >= mlen) {
-          for (uint32_t k = B2S_LANE; k < mlen; k += B2S_NLANES) d[k] = s[k];
-        } else {  // overlapping match: every byte comes from the already complete window [d - offset, d)
-          for (uint32_t k = B2S_LANE; k < mlen; k += B2S_NLANES) d[k] = s[k % offset];
-        }
-        B2S_SYNC();
+        for (uint32_t k = 0; k < mlen; k++) d[k] = s[k];
+#endif
       }
       lpos += llen;
       produced += (uint64_t)llen + mlen;
