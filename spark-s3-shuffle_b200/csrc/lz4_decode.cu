@@ -43,16 +43,31 @@ __global__ void __launch_bounds__(64) lz4_tokens_kernel(const BlockDesc* __restr
   bool err = false;
   int pf_sector = -1;
   for (int k = 64; k < 512 && k < clen; k += 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + k));
-  for (;;) {
+  // The token chain is what bounds this kernel (one dependent L1 round trip per field).  Every sequence therefore
+  // starts with ONE 8-byte window read at ip — three independent aligned word loads — which holds the token, and for
+  // the common short sequence (literals <= 5) also the offset: one round trip instead of two or three.
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(in);
+  while (true) {
     if (ip >= clen) {
       err = true;
       break;
     }
-    if ((ip >> 5) != pf_sector) {  // entering a new 32-byte sector: each lane streams its own block, so pull the
-      pf_sector = ip >> 5;         // sector 16 ahead towards L1/L2 now (a miss is a DRAM round trip otherwise)
+    if ((ip >> 5) != pf_sector) {  // entering a new 32-byte sector: pull the sector 16 ahead towards L1/L2 now
+      pf_sector = ip >> 5;
       if (ip + 512 < clen) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + ip + 512));
     }
-    const int token = __ldg(in + ip++);
+    // window: bytes ip .. ip+7 (only aligned words that contain bytes of the block are read: ip + 7 may pass the end
+    // of the block by < 8 bytes, inside the same or the next aligned word of the arena's 256-byte granule)
+    const uintptr_t wa = a0 + (uintptr_t)ip;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(wa & ~uintptr_t(3));
+    const unsigned wsh = (wa & 3u) * 8u;
+    const int avail = clen - ip;  // >= 1
+    const uint32_t x0 = __ldg(wp);
+    const uint32_t x1 = ((int)(wa & 3u) + avail > 4) ? __ldg(wp + 1) : 0u;
+    const uint32_t x2 = ((int)(wa & 3u) + avail > 8) ? __ldg(wp + 2) : 0u;
+    const uint32_t lo = __funnelshift_r(x0, x1, wsh), hi = __funnelshift_r(x1, x2, wsh);
+    const int token = (int)(lo & 0xffu);
+    ip++;
     int ll = token >> 4;
     if (ll == 15) {
       int bb;
@@ -82,7 +97,14 @@ __global__ void __launch_bounds__(64) lz4_tokens_kernel(const BlockDesc* __restr
       err = true;
       break;
     }
-    const int off = __ldg(in + ip) | (__ldg(in + ip + 1) << 8);
+    int off;
+    if (ll <= 5 && (token >> 4) != 15) {  // offset bytes sit at window bytes 1+ll, 2+ll (<= 7)
+      const unsigned sb = 8u * (unsigned)(1 + ll);
+      const uint32_t w = sb < 32 ? __funnelshift_r(lo, hi, sb) : hi >> (sb - 32);
+      off = (int)(w & 0xffffu);
+    } else {
+      off = __ldg(in + ip) | (__ldg(in + ip + 1) << 8);
+    }
     ip += 2;
     int ml = token & 15;
     if (ml == 15) {
