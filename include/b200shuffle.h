@@ -60,12 +60,16 @@ extern "C" {
 #define B2S_E_NOMEM (-8)
 
 /* ---- lifecycle: call once per executor, beside S3ShuffleDataIO.initializeExecutor (shuffle/S3ShuffleDataIO.scala:30-32) ---- */
-/* gpu_mask: bit i selects CUDA device i (0 = all visible devices).  Blocks of a batch are sharded round-robin
- * over the selected devices.  pinned_bytes_per_gpu sizes the pinned staging ring used when caller memory is
- * pageable (0 = default 256 MiB).  streams_per_gpu 0 = default 2.  Idempotent. */
+/* gpu_mask: bit i selects CUDA device i (0 = all visible devices).  The per-stream-pointer calls (b2s_*_batch) shard
+ * their streams round-robin over the selected devices (stream i -> device i mod D), one host thread, pinned staging and
+ * streams per device, nothing exchanged between devices.  Packed and device-resident calls run on ONE device: the calling
+ * thread's (b2s_set_thread_device, default 0) — an executor pins each task thread to a device, or, as bench.py does,
+ * runs one process per GPU.  pinned_bytes_per_gpu / streams_per_gpu are accepted for compatibility; staging and slots
+ * are sized automatically.  Idempotent. */
 int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_per_gpu);
 void b2s_shutdown(void);
 int b2s_device_count(void); /* devices selected by b2s_init, or B2S_E_NOT_INIT */
+int b2s_set_thread_device(uint32_t dev_index); /* device used by this thread's packed / host-pointer calls */
 const char* b2s_strerror(int32_t code);
 const char* b2s_last_error(void); /* thread-local text of the last B2S_E_CUDA / B2S_E_ARG */
 uint32_t b2s_version(void);

@@ -37,6 +37,7 @@ PROTOTYPES = [
     ("b2s_init", C.c_int, [_u32, _u64, _u32]),
     ("b2s_shutdown", None, []),
     ("b2s_device_count", C.c_int, []),
+    ("b2s_set_thread_device", C.c_int, [_u32]),
     ("b2s_strerror", C.c_char_p, [_i32]),
     ("b2s_last_error", C.c_char_p, []),
     ("b2s_version", _u32, []),

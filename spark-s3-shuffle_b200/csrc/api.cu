@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -25,6 +26,7 @@ namespace {
 
 thread_local std::string t_last_error;
 thread_local b2s_timing t_timing;
+thread_local uint32_t t_device = 0;  // device (index into the b2s_init selection) used by this thread's host-pointer calls
 
 int fail(int code, const char* fmt, const char* a = "") {
   char buf[512];
@@ -652,6 +654,54 @@ uint64_t plan_runs(uint32_t cnt, const uint8_t* const* ptr, const uint64_t* len,
   return cur;
 }
 
+
+// ---- in-process multi-GPU: the per-stream-pointer batch calls shard their streams round-robin (stream i -> device
+// i mod D) over every device selected by b2s_init, one host thread per device, each driving its own pipeline slots,
+// pinned staging and streams; nothing is exchanged between devices.  Packed calls and the calling
+// thread's own work stay on the thread's device (b2s_set_thread_device).
+template <typename F>
+int shard_over_devices(uint32_t n, F&& run_subset) {
+  const uint32_t D = g_ctx ? (uint32_t)g_ctx->devs.size() : 0;
+  std::vector<int> rcs(D, 0);
+  std::vector<std::string> errs(D);
+  std::vector<b2s_timing> tms(D);
+  std::vector<std::thread> th;
+  for (uint32_t d = 0; d < D; d++) {
+    th.emplace_back([&, d] {
+      t_device = d;
+      std::vector<uint32_t> idx;
+      for (uint32_t i = d; i < n; i += D) idx.push_back(i);
+      rcs[d] = idx.empty() ? 0 : run_subset(idx);
+      errs[d] = t_last_error;
+      tms[d] = t_timing;
+    });
+  }
+  for (auto& t : th) t.join();
+  t_timing = b2s_timing{};
+  int rc = 0;
+  for (uint32_t d = 0; d < D; d++) {
+    if (rcs[d] && !rc) {
+      rc = rcs[d];
+      t_last_error = errs[d];
+    }
+    // devices work concurrently: times are the slowest device's, byte and launch counters add up
+    t_timing.total_ms = std::max(t_timing.total_ms, tms[d].total_ms);
+    t_timing.h2d_ms = std::max(t_timing.h2d_ms, tms[d].h2d_ms);
+    t_timing.d2h_ms = std::max(t_timing.d2h_ms, tms[d].d2h_ms);
+    t_timing.kernel_ms = std::max(t_timing.kernel_ms, tms[d].kernel_ms);
+    t_timing.top_kernel_ms = std::max(t_timing.top_kernel_ms, tms[d].top_kernel_ms);
+    t_timing.dominant_ms = std::max(t_timing.dominant_ms, tms[d].dominant_ms);
+    t_timing.h2d_bytes += tms[d].h2d_bytes;
+    t_timing.d2h_bytes += tms[d].d2h_bytes;
+    t_timing.kernel_launches += tms[d].kernel_launches;
+    t_timing.dominant_launches += tms[d].dominant_launches;
+    t_timing.src_bytes += tms[d].src_bytes;
+    t_timing.dst_bytes += tms[d].dst_bytes;
+  }
+  return rc;
+}
+bool want_sharding(uint32_t n) { return g_ctx && g_ctx->devs.size() > 1 && n >= 2 * g_ctx->devs.size(); }
+
 }  // namespace
 
 // ==============================================================================================================
@@ -759,6 +809,13 @@ void b2s_shutdown(void) {
 }
 
 int b2s_device_count(void) { return g_ctx ? (int)g_ctx->devs.size() : B2S_E_NOT_INIT; }
+
+int b2s_set_thread_device(uint32_t dev_index) {
+  if (!g_ctx) return fail(B2S_E_NOT_INIT, "b2s_init has not been called%s");
+  if (dev_index >= g_ctx->devs.size()) return fail(B2S_E_ARG, "device index out of range%s");
+  t_device = dev_index;
+  return 0;
+}
 
 void* b2s_host_alloc(uint64_t bytes) {
   void* p = nullptr;
@@ -921,7 +978,7 @@ static int checksum_host(uint32_t alg, uint32_t n, const uint8_t* const* ptr, co
   WallTimer wt;
   t_timing = b2s_timing{};
   Device* D;
-  int rc = get_device(0, &D);
+  int rc = get_device(t_device, &D);
   if (rc) return rc;
   if (!n) return 0;
   std::lock_guard<std::mutex> lk(D->mtx);
@@ -956,9 +1013,23 @@ static int checksum_host(uint32_t alg, uint32_t n, const uint8_t* const* ptr, co
   return 0;
 }
 
+
 int b2s_checksum_batch(uint32_t alg, uint32_t n, const uint8_t* const* src, const uint64_t* len, uint64_t* out) {
   if (n && (!src || !len || !out)) return fail(B2S_E_ARG, "null argument%s");
-  return checksum_host(alg, n, src, len, out);
+  if (!want_sharding(n)) return checksum_host(alg, n, src, len, out);
+  return shard_over_devices(n, [&](const std::vector<uint32_t>& idx) {
+    const uint32_t m = (uint32_t)idx.size();
+    std::vector<const uint8_t*> p(m);
+    std::vector<uint64_t> l(m), o(m);
+    for (uint32_t k = 0; k < m; k++) {
+      p[k] = src[idx[k]];
+      l[k] = len[idx[k]];
+    }
+    int rc = checksum_host(alg, m, p.data(), l.data(), o.data());
+    if (!rc)
+      for (uint32_t k = 0; k < m; k++) out[idx[k]] = o[k];
+    return rc;
+  });
 }
 int b2s_checksum_packed(uint32_t alg, uint32_t n, const uint8_t* base, const uint64_t* off, const uint64_t* len,
                         uint64_t* out) {
@@ -1027,7 +1098,7 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
   WallTimer wt;
   t_timing = b2s_timing{};
   Device* D;
-  int rc = get_device(0, &D);
+  int rc = get_device(t_device, &D);
   if (rc) return rc;
   if (alg > B2S_CHECKSUM_CRC32C) return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
   if (dst_total) *dst_total = 0;
@@ -1140,9 +1211,33 @@ int b2s_compress_batch(uint32_t codec, int32_t level, uint32_t codec_block_size,
                        const uint64_t* dst_cap, uint64_t* dst_len, uint64_t* checksum_out, int32_t* status) {
   (void)level;
   if (n && (!src || !src_len || !dst || !dst_cap || !dst_len || !status)) return fail(B2S_E_ARG, "null argument%s");
-  std::vector<uint64_t> off(n);
-  return compress_host(codec, codec_block_size, checksum_alg, n, src, src_len, nullptr, 0, dst, dst_cap, off.data(),
-                       dst_len, nullptr, checksum_out, status);
+  if (!want_sharding(n)) {
+    std::vector<uint64_t> off(n);
+    return compress_host(codec, codec_block_size, checksum_alg, n, src, src_len, nullptr, 0, dst, dst_cap, off.data(),
+                         dst_len, nullptr, checksum_out, status);
+  }
+  return shard_over_devices(n, [&](const std::vector<uint32_t>& idx) {
+    const uint32_t m = (uint32_t)idx.size();
+    std::vector<const uint8_t*> sp(m);
+    std::vector<uint8_t*> dp(m);
+    std::vector<uint64_t> sl(m), dc(m), dl(m), ck(m), off(m);
+    std::vector<int32_t> st(m);
+    for (uint32_t k = 0; k < m; k++) {
+      sp[k] = src[idx[k]];
+      sl[k] = src_len[idx[k]];
+      dp[k] = dst[idx[k]];
+      dc[k] = dst_cap[idx[k]];
+    }
+    int rc = compress_host(codec, codec_block_size, checksum_alg, m, sp.data(), sl.data(), nullptr, 0, dp.data(),
+                           dc.data(), off.data(), dl.data(), nullptr, ck.data(), st.data());
+    if (!rc)
+      for (uint32_t k = 0; k < m; k++) {
+        dst_len[idx[k]] = dl[k];
+        status[idx[k]] = st[k];
+        if (checksum_out) checksum_out[idx[k]] = ck[k];
+      }
+    return rc;
+  });
 }
 
 int b2s_compress_packed(uint32_t codec, int32_t level, uint32_t codec_block_size, uint32_t checksum_alg, uint32_t n,
@@ -1249,7 +1344,7 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
   WallTimer wt;
   t_timing = b2s_timing{};
   Device* D;
-  int rc = get_device(0, &D);
+  int rc = get_device(t_device, &D);
   if (rc) return rc;
   if (alg > B2S_CHECKSUM_CRC32C) return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
   if (dst_total) *dst_total = 0;
@@ -1390,9 +1485,43 @@ int b2s_decompress_batch(uint32_t codec, uint32_t checksum_alg, uint32_t n, cons
   if (checksum_alg && n && (!n_slices || !slice_len || !slice_checksum)) return fail(B2S_E_ARG, "slice arrays required%s");
   std::vector<uint32_t> base;
   std::vector<uint64_t> len, sum;
-  if (checksum_alg) flatten_slices(n, n_slices, slice_len, slice_checksum, base, len, sum);
-  return decompress_host(codec, checksum_alg, n, src, src_len, base.data(), len.data(), sum.data(), nullptr, 0, dst,
-                         dst_cap, nullptr, dst_len, nullptr, status, bad_slice, false);
+  if (!want_sharding(n)) {
+    if (checksum_alg) flatten_slices(n, n_slices, slice_len, slice_checksum, base, len, sum);
+    return decompress_host(codec, checksum_alg, n, src, src_len, base.data(), len.data(), sum.data(), nullptr, 0, dst,
+                           dst_cap, nullptr, dst_len, nullptr, status, bad_slice, false);
+  }
+  return shard_over_devices(n, [&](const std::vector<uint32_t>& idx) {
+    const uint32_t m = (uint32_t)idx.size();
+    std::vector<const uint8_t*> sp(m);
+    std::vector<uint8_t*> dp(m);
+    std::vector<uint64_t> sl(m), dc(m), dl(m);
+    std::vector<uint32_t> ns(m), b;
+    std::vector<const uint64_t*> slp(m), scp(m);
+    std::vector<uint64_t> l, c;
+    std::vector<int32_t> st(m), bad(m);
+    for (uint32_t k = 0; k < m; k++) {
+      const uint32_t i = idx[k];
+      sp[k] = src[i];
+      sl[k] = src_len[i];
+      dp[k] = dst[i];
+      dc[k] = dst_cap[i];
+      if (checksum_alg) {
+        ns[k] = n_slices[i];
+        slp[k] = slice_len[i];
+        scp[k] = slice_checksum[i];
+      }
+    }
+    if (checksum_alg) flatten_slices(m, ns.data(), slp.data(), scp.data(), b, l, c);
+    int rc = decompress_host(codec, checksum_alg, m, sp.data(), sl.data(), b.data(), l.data(), c.data(), nullptr, 0,
+                             dp.data(), dc.data(), nullptr, dl.data(), nullptr, st.data(), bad.data(), false);
+    if (!rc)
+      for (uint32_t k = 0; k < m; k++) {
+        dst_len[idx[k]] = dl[k];
+        status[idx[k]] = st[k];
+        if (bad_slice) bad_slice[idx[k]] = bad[k];
+      }
+    return rc;
+  });
 }
 
 int b2s_decompress_packed(uint32_t codec, uint32_t checksum_alg, uint32_t n, const uint8_t* src_base,

@@ -549,11 +549,7 @@ static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, c
                            uint32_t block_size, uint32_t stride, uint32_t near_limit, uint16_t* d_off,
                            uint16_t* d_ml, unsigned int* d_counter, cudaStream_t st) {
   const size_t smem = (size_t)kMatchWarps * (2u << HLOG);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(lz4_match_kernel<HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(lz4_match_kernel<HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device and cheap: set on every launch
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_match_kernel<HLOG>, kMatchWarps * 32, smem);
   if (per_sm < 1) per_sm = 1;

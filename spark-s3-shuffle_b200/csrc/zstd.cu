@@ -83,11 +83,7 @@ static void launch_zstd_t(const uint8_t* src_base, const uint64_t* d_src_off, co
                           uint64_t dst_cap, int32_t* d_status, cudaStream_t st) {
   const uint32_t workers = zstd_workers(n);
   const size_t smem = (size_t)kZWarps * sizeof(zstd::Workspace);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(zstd_stream_kernel<SIZE_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(zstd_stream_kernel<SIZE_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device and cheap: set on every launch
   zstd_stream_kernel<SIZE_ONLY><<<(workers + kZWarps - 1) / kZWarps, kZWarps * 32, smem, st>>>(
       src_base, d_src_off, d_src_len, n, d_ws, workers, d_olen, dst_base, d_dst_off, dst_cap, d_status);
 }
