@@ -79,11 +79,12 @@ def build_host(force=False):
     """libb200shuffle_host.so: the C++ host mirror of the reference's writer/reader/helper classes, linked against
     the C ABI (g++ only; it contains no device code)."""
     lib = build(force=force)
+    import glob
     deps = [HOST_SRC, os.path.join(HERE, "..", "include", "b200shuffle_host.h"),
-            os.path.join(HERE, "..", "include", "b200shuffle.h"), lib]
+            os.path.join(HERE, "..", "include", "b200shuffle.h"), lib] + glob.glob(os.path.join(HERE, "host", "*.h"))
     if not force and os.path.exists(HOST_LIB) and os.path.getmtime(HOST_LIB) >= max(os.path.getmtime(d) for d in deps):
         return HOST_LIB
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB, HOST_SRC, "-L" + HERE,
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread", "-o", HOST_LIB, HOST_SRC, "-L" + HERE,
            "-l:libb200shuffle.so", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

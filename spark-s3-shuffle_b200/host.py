@@ -58,7 +58,34 @@ PROTOTYPES = [
      [_vp, _u32, C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_u64)]),
     ("b2sh_reader_remote_bytes_read", _u64, [_vp]),
     ("b2sh_reader_destroy", None, [_vp]),
+    ("b2sh_writer_statistics", C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.c_char_p, _u32]),
+    ("b2sh_reader_open", C.c_int, [_vp]),
+    ("b2sh_reader_next_batch", C.c_int, [_vp, _u32, C.POINTER(_u32)]),
+    ("b2sh_reader_statistics", C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.c_char_p, _u32]),
+    ("b2sh_prefetch_create", C.c_int, [_vp, _i32, _vp, _u32, _i32, _i32, C.c_int, _i64, _i32, C.POINTER(_vp)]),
+    ("b2sh_prefetch_has_next", C.c_int, [_vp]),
+    ("b2sh_prefetch_next", C.c_int,
+     [_vp, C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_u64), C.POINTER(_u64)]),
+    ("b2sh_prefetch_close_stream", C.c_int, [_vp, _u64]),
+    ("b2sh_prefetch_statistics", C.c_int, [_vp, C.POINTER(_u64), C.c_char_p, _u32]),
+    ("b2sh_prefetch_destroy", None, [_vp]),
+    ("b2sh_codec_create", C.c_int, [_vp, C.POINTER(_vp)]),
+    ("b2sh_codec_supports_concatenation", C.c_int, [_vp]),
+    ("b2sh_codec_destroy", None, [_vp]),
+    ("b2sh_codec_output_stream", C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    ("b2sh_ostream_write", C.c_int, [_vp, _vp, _u64]),
+    ("b2sh_ostream_flush", C.c_int, [_vp]),
+    ("b2sh_ostream_close", C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u32)]),
+    ("b2sh_ostream_destroy", None, [_vp]),
+    ("b2sh_codec_input_stream", C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    ("b2sh_istream_read", C.c_int, [_vp, _vp, _u64, C.POINTER(_i64)]),
+    ("b2sh_istream_close", C.c_int, [_vp]),
+    ("b2sh_istream_destroy", None, [_vp]),
 ]
+SINK_FN = C.CFUNCTYPE(_i64, _vp, _vp, _u64)
+SOURCE_FN = C.CFUNCTYPE(_i64, _vp, _vp, _u64)
+STAT_KEYS = ("bytesRead", "numStreams", "timeWaiting", "timePrefetching", "totalRuntime", "activeThreads",
+             "peakMemoryUsage", "peakThreads")
 SYMBOLS = [p[0] for p in PROTOTYPES]
 _lib = None
 
@@ -177,6 +204,12 @@ class S3ShuffleMapOutputWriter:
     def abort(self):
         _check(load().b2sh_writer_abort(self._h))
 
+    def statistics(self):
+        """S3MeasureOutputStream's counters for the .data stream: (bytes, nanoseconds, log line)"""
+        b, ns, line = _u64(), _u64(), C.create_string_buffer(512)
+        _check(load().b2sh_writer_statistics(self._h, C.byref(b), C.byref(ns), line, 512))
+        return b.value, ns.value, line.value.decode()
+
     def close(self):
         if self._h:
             load().b2sh_writer_destroy(self._h)
@@ -209,13 +242,31 @@ class S3ShuffleReader:
     def read(self):
         n = _u32(0)
         _check(load().b2sh_reader_read(self._h, C.byref(n)))
+        return self._blocks(n.value)
+
+    def _blocks(self, n):
         out = []
-        for k in range(n.value):
+        for k in range(n):
             m, rs, re, p, ln = _i64(), _i32(), _i32(), _vp(), _u64()
             _check(load().b2sh_reader_block(self._h, k, C.byref(m), C.byref(rs), C.byref(re), C.byref(p), C.byref(ln)))
-            data = C.string_at(p.value, ln.value) if ln.value else b""
-            out.append(((m.value, rs.value, re.value), data))
+            out.append(((m.value, rs.value, re.value), C.string_at(p.value, ln.value) if ln.value else b""))
         return out
+
+    def open(self):
+        """start the prefetcher (storage/S3BufferedPrefetchIterator.scala); then call nextBatch() until it returns None"""
+        _check(load().b2sh_reader_open(self._h))
+
+    def nextBatch(self, maxBlocks=0):
+        n = _u32(0)
+        _check(load().b2sh_reader_next_batch(self._h, maxBlocks, C.byref(n)))
+        return self._blocks(n.value) if n.value else None
+
+    def statistics(self):
+        v, nb, line = (_u64 * 8)(), _u64(), C.create_string_buffer(1024)
+        _check(load().b2sh_reader_statistics(self._h, v, C.byref(nb), line, 1024))
+        d = dict(zip(STAT_KEYS, list(v)))
+        d["batches"], d["line"] = nb.value, line.value.decode()
+        return d
 
     @property
     def remoteBytesRead(self):
@@ -224,4 +275,140 @@ class S3ShuffleReader:
     def close(self):
         if self._h:
             load().b2sh_reader_destroy(self._h)
+            self._h = None
+
+
+class S3BufferedPrefetchIterator:
+    """storage/S3BufferedPrefetchIterator.scala on its own: yields ((mapId, startReduce, endReduce), compressed bytes,
+    stream handle); the block stays charged to the budget until closeStream(handle)."""
+
+    def __init__(self, dispatcher, shuffleId, mapIds, startPartition, endPartition, doBatchFetch=False,
+                 maxBufferSize=0, maxThreads=0):
+        self._h = _vp()
+        ids = np.ascontiguousarray(mapIds, dtype=np.int64)
+        _check(load().b2sh_prefetch_create(dispatcher._h, shuffleId, ids.ctypes.data, ids.size, startPartition,
+                                           endPartition, int(doBatchFetch), maxBufferSize, maxThreads,
+                                           C.byref(self._h)))
+
+    def hasNext(self):
+        return bool(load().b2sh_prefetch_has_next(self._h))
+
+    def next(self):
+        m, rs, re, p, ln, h = _i64(), _i32(), _i32(), _vp(), _u64(), _u64()
+        _check(load().b2sh_prefetch_next(self._h, C.byref(m), C.byref(rs), C.byref(re), C.byref(p), C.byref(ln),
+                                         C.byref(h)))
+        return (m.value, rs.value, re.value), (C.string_at(p.value, ln.value) if ln.value else b""), h.value
+
+    def closeStream(self, handle):
+        _check(load().b2sh_prefetch_close_stream(self._h, handle))
+
+    def statistics(self):
+        v, line = (_u64 * 8)(), C.create_string_buffer(1024)
+        _check(load().b2sh_prefetch_statistics(self._h, v, line, 1024))
+        d = dict(zip(STAT_KEYS, list(v)))
+        d["line"] = line.value.decode()
+        return d
+
+    def close(self):
+        if self._h:
+            load().b2sh_prefetch_destroy(self._h)
+            self._h = None
+
+
+class B200CompressionCodec:
+    """The Spark CompressionCodec seam: compressedOutputStream(sink) / compressedInputStream(source)
+    over file-like objects.  Codec and block size come from the dispatcher's conf."""
+
+    class _Out:
+        def __init__(self, codec, sink):
+            self._sink, self._err = sink, None
+
+            def cb(ctx, p, n):
+                try:
+                    sink.write(C.string_at(p, n))
+                    return n
+                except Exception as e:  # surfaces as IOException from the C side
+                    self._err = e
+                    return -1
+
+            self._cb = SINK_FN(cb)
+            self._h = _vp()
+            _check(load().b2sh_codec_output_stream(codec._h, C.cast(self._cb, _vp), None, C.byref(self._h)))
+            self.bytesIn = self.bytesOut = self.streams = 0
+
+        def write(self, data):
+            a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+            _check(load().b2sh_ostream_write(self._h, a.ctypes.data if a.size else None, a.size))
+
+        def flush(self):
+            _check(load().b2sh_ostream_flush(self._h))
+
+        def close(self):
+            if not self._h:
+                return
+            bi, bo, ns = _u64(), _u64(), _u32()
+            try:
+                _check(load().b2sh_ostream_close(self._h, C.byref(bi), C.byref(bo), C.byref(ns)))
+                self.bytesIn, self.bytesOut, self.streams = bi.value, bo.value, ns.value
+            finally:
+                load().b2sh_ostream_destroy(self._h)
+                self._h = None
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            self.close()
+
+    class _In:
+        def __init__(self, codec, source):
+            def cb(ctx, p, cap):
+                b = source.read(min(cap, 1 << 24))
+                if not b:
+                    return 0
+                C.memmove(p, b, len(b))
+                return len(b)
+
+            self._cb = SOURCE_FN(cb)
+            self._h = _vp()
+            _check(load().b2sh_codec_input_stream(codec._h, C.cast(self._cb, _vp), None, C.byref(self._h)))
+
+        def read(self, n=-1):
+            """n < 0: everything that is left; else up to n bytes (b"" at the end, like a Python file object)"""
+            out = []
+            want = n
+            while want != 0:
+                k = (1 << 24) if want < 0 else min(want, 1 << 24)
+                buf = np.empty(k, dtype=np.uint8)
+                got = _i64()
+                _check(load().b2sh_istream_read(self._h, buf.ctypes.data, k, C.byref(got)))
+                if got.value < 0:
+                    break
+                out.append(buf[: got.value].tobytes())
+                if want > 0:
+                    want -= got.value
+            return b"".join(out)
+
+        def close(self):
+            if self._h:
+                load().b2sh_istream_close(self._h)
+                load().b2sh_istream_destroy(self._h)
+                self._h = None
+
+    def __init__(self, dispatcher):
+        self._h = _vp()
+        _check(load().b2sh_codec_create(dispatcher._h, C.byref(self._h)))
+
+    def supportsConcatenationOfSerializedStreams(self):
+        return bool(load().b2sh_codec_supports_concatenation(self._h))
+
+    def compressedOutputStream(self, sink):
+        return self._Out(self, sink)
+
+    def compressedInputStream(self, source):
+        return self._In(self, source)
+
+    def close(self):
+        if self._h:
+            load().b2sh_codec_destroy(self._h)
             self._h = None

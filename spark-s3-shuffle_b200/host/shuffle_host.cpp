@@ -57,6 +57,7 @@ class PinnedArena {
   ~PinnedArena() { release(p_, pinned_); }
   uint8_t* data() { return p_; }
   uint64_t size() const { return n_; }
+  uint64_t capacity() const { return cap_; }
   void clear() { n_ = 0; }
   void reserve(uint64_t cap) {
     if (cap <= cap_) return;
@@ -108,6 +109,13 @@ static void mkdirs(const std::string& dir) {
   }
 }
 
+}  // namespace host
+}  // namespace b2s
+#include "streams.h"
+#include "codec_adapter.h"
+namespace b2s {
+namespace host {
+
 // ---- S3ShuffleDispatcher (helper/S3ShuffleDispatcher.scala) -------------------------------------------------
 class S3ShuffleDispatcher {
  public:
@@ -138,6 +146,8 @@ class S3ShuffleDispatcher {
     codecName = get("spark.io.compression.codec", "lz4");
     lz4BlockSize = (uint32_t)getSize("spark.io.compression.lz4.blockSize", 32 * 1024);
     gpuEnabled = getBool("spark.shuffle.s3.gpu.enabled", true);  // additive key
+    gpuCodecBufferSize = (uint64_t)getSize("spark.shuffle.s3.gpu.codecBufferSize", 64L * 1024 * 1024);  // additive
+    gpuReadBatchBlocks = getInt("spark.shuffle.s3.gpu.readBatchBlocks", 0);  // additive; 0 = all completed blocks
     if (!rootIsLocal && rootDir.find("://") != std::string::npos)
       throw UnsupportedOperationException("only file:// roots are implemented by the host mirror: " + rootDir);
   }
@@ -177,6 +187,8 @@ class S3ShuffleDispatcher {
        gpuEnabled = true;
   int bufferSize = 0, maxBufferSizeTask = 0, maxConcurrencyTask = 0, folderPrefixes = 10;
   uint32_t lz4BlockSize = 32768;
+  uint64_t gpuCodecBufferSize = 64ull << 20;
+  int gpuReadBatchBlocks = 0;
 
   // caches of S3ShuffleHelper (helper/S3ShuffleHelper.scala:15-16) live with the dispatcher instance here
   std::mutex cacheMutex;
@@ -376,9 +388,12 @@ class S3ShuffleMapOutputWriter {
     if (lastPartitionWriterId_ >= 0) {  // the .data object exists as soon as a stream was opened (:43-49)
       std::string path = d_.getPath(BlockId{BlockId::Data, shuffleId_, mapId_, 0, 0});
       mkdirs(path.substr(0, path.rfind('/')));
-      std::ofstream f(path, std::ios::binary | std::ios::trunc);
-      if (!f) throw IOException("cannot create " + path);
-      f.write((const char*)data, (std::streamsize)data_len);
+      // initStream (:43-49): BufferedOutputStream(S3MeasureOutputStream(createBlock(shuffleBlock), name), bufferSize)
+      measure_.reset(new S3MeasureOutputStream(path, BlockId{BlockId::Data, shuffleId_, mapId_, 0, 0}.name(),
+                                               (size_t)d_.bufferSize));
+      measure_->write(data, data_len);
+      measure_->flush();  // :102-107
+      measure_->close();
     }
     if (sum > 0 || d_.alwaysCreateIndex) {  // :111
       S3ShuffleHelper::writePartitionLengths(d_, shuffleId_, mapId_, partitionLengths_);
@@ -390,6 +405,7 @@ class S3ShuffleMapOutputWriter {
     buf_.clear();
     streamOpen_ = false;
   }
+  const S3MeasureOutputStream* measure() const { return measure_.get(); }
 
  private:
   S3ShuffleDispatcher& d_;
@@ -401,6 +417,7 @@ class S3ShuffleMapOutputWriter {
   int32_t lastPartitionWriterId_ = -1, current_ = -1;
   bool streamOpen_ = false, gpu_ = true;
   PinnedArena buf_, out_;
+  std::unique_ptr<S3MeasureOutputStream> measure_;
 };
 
 // ---- S3SingleSpillShuffleMapOutputWriter (shuffle/S3SingleSpillShuffleMapOutputWriter.scala:24-64) ------------------
@@ -467,104 +484,174 @@ class S3SingleSpillShuffleMapOutputWriter {
   int64_t mapId_;
 };
 
-// ---- S3ShuffleReader (storage/S3ShuffleReader.scala + block iterator/stream + checksum validation) ---------
+// ---- S3ShuffleReader (storage/S3ShuffleReader.scala + block iterator/stream + prefetcher + checksum validation) ---
+// The slices of a block (one per reduce partition it covers) travel with it, so that the per-partition validation of
+// S3ChecksumValidationStream (storage/S3ChecksumValidationStream.scala:54-86) runs on the GPU inside the same batch
+// call that decodes the block: verify first, then decompress, the reference's order (:99-110).
+struct ShuffleBlockInfo {
+  BlockId id;
+  std::vector<uint64_t> sliceLen, sliceSum;
+};
+
+// computeShuffleBlocks (storage/S3ShuffleReader.scala:160-197, file-listing variant) + S3ShuffleBlockIterator
+// (storage/S3ShuffleBlockIterator.scala:36-43) + filterNot(maxBytes == 0) and the read metrics (:89-97)
+static std::deque<S3BufferedPrefetchIterator::Source> computeShuffleBlockStreams(
+    S3ShuffleDispatcher& d, int32_t shuffleId, const std::vector<int64_t>& mapIds, int32_t start, int32_t end,
+    bool batch, std::vector<ShuffleBlockInfo>& info, uint64_t& remoteBytesRead, uint64_t& remoteBlocksFetched) {
+  std::deque<S3BufferedPrefetchIterator::Source> out;
+  const bool verify = d.checksumEnabled;
+  for (int64_t mapId : mapIds) {
+    std::vector<int64_t> acc = S3ShuffleHelper::getPartitionLengths(d, shuffleId, mapId);
+    if ((int)acc.size() < end + 1)
+      throw SparkException("index of map " + std::to_string(mapId) + " has too few partitions");
+    std::vector<int64_t> sums;
+    if (verify) sums = S3ShuffleHelper::getChecksums(d, shuffleId, mapId);
+    std::vector<std::pair<int32_t, int32_t>> ranges;
+    if (batch && end - start > 1) ranges.push_back({start, end});
+    else for (int32_t r = start; r < end; r++) ranges.push_back({r, r + 1});
+    const std::string path = d.getPath(BlockId{BlockId::Data, shuffleId, mapId, 0, 0});
+    for (auto [rs, re] : ranges) {
+      const int64_t a = acc[(size_t)rs], b = acc[(size_t)re];
+      if (b - a == 0) continue;                // filterNot(_._2.maxBytes == 0)  (:91)
+      remoteBytesRead += (uint64_t)(b - a);    // incRemoteBytesRead (:94)
+      remoteBlocksFetched += 1;                // incRemoteBlocksFetched (:95)
+      ShuffleBlockInfo bi;
+      bi.id = (re - rs > 1) ? BlockId{BlockId::ShuffleBatch, shuffleId, mapId, rs, re}
+                            : BlockId{BlockId::Shuffle, shuffleId, mapId, rs, re};
+      if (verify)
+        for (int32_t r = rs; r < re; r++) {    // S3ChecksumValidationStream walks the .index differences (:68-86)
+          bi.sliceLen.push_back((uint64_t)(acc[(size_t)r + 1] - acc[(size_t)r]));
+          bi.sliceSum.push_back((uint64_t)sums[(size_t)r]);
+        }
+      S3BufferedPrefetchIterator::Source src;
+      src.id = bi.id;
+      src.stream.reset(new S3ShuffleBlockStream(path, a, b));
+      src.tag = info.size();
+      info.push_back(std::move(bi));
+      out.push_back(std::move(src));
+    }
+  }
+  return out;
+}
+
 class S3ShuffleReader {
  public:
   struct Block {
     BlockId id;
-    uint64_t srcOff = 0, srcLen = 0;    // in the fetched arena
-    uint64_t dstOff = 0, dstLen = 0;    // in the decoded arena
+    const uint8_t* data = nullptr;
+    uint64_t len = 0;
   };
   S3ShuffleReader(S3ShuffleDispatcher& d, int32_t shuffleId, std::vector<int64_t> mapIds, int32_t startPartition,
                   int32_t endPartition, bool doBatchFetch)
       : d_(d), shuffleId_(shuffleId), mapIds_(std::move(mapIds)), start_(startPartition), end_(endPartition),
         batch_(doBatchFetch || d.forceBatchFetch) {}
+  ~S3ShuffleReader() { iter_.reset(); }
 
-  // read(): storage/S3ShuffleReader.scala:77-110
+  // read(): storage/S3ShuffleReader.scala:77-110 — everything the task reads, drained batch by batch
   void read() {
+    open();
+    std::vector<Block> all;
+    std::vector<std::unique_ptr<uint8_t[]>> bufs;
+    while (nextBatch((size_t)d_.gpuReadBatchBlocks)) {
+      all.insert(all.end(), blocks_.begin(), blocks_.end());
+      for (auto& p : decoded_) bufs.push_back(std::move(p));
+      decoded_.clear();
+    }
+    blocks_ = std::move(all);
+    decoded_ = std::move(bufs);
+  }
+
+  void open() {
+    iter_.reset();
+    info_.clear();
     blocks_.clear();
-    remoteBytesRead_ = 0;
+    decoded_.clear();
+    remoteBytesRead_ = remoteBlocksFetched_ = 0;
+    batches_ = 0;
+    if (d_.codecId() == B2S_CODEC_NONE)
+      throw UnsupportedOperationException("spark.shuffle.compress=false is served by the stock reader path");
+    auto src = computeShuffleBlockStreams(d_, shuffleId_, mapIds_, start_, end_, batch_, info_, remoteBytesRead_,
+                                          remoteBlocksFetched_);
+    iter_.reset(new S3BufferedPrefetchIterator(std::move(src), d_.maxBufferSizeTask, d_.maxConcurrencyTask));
+  }
+
+  // drain the blocks the prefetcher has completed, verify + decode them in ONE C-ABI batch, give
+  // their buffers back to the prefetcher's budget.  Returns false when the task has no more blocks.
+  bool nextBatch(size_t maxBlocks) {
+    if (!iter_) throw RuntimeException("reader is not open");
+    blocks_.clear();
+    decoded_.clear();
+    if (!iter_->hasNext()) {
+      stats_ = iter_->statistics();
+      return false;
+    }
+    std::vector<S3BufferedPrefetchIterator::Fetched> got = iter_->nextBatch(maxBlocks);
+    const uint32_t n = (uint32_t)got.size();
     const bool verify = d_.checksumEnabled;
     const uint32_t alg = verify ? S3ShuffleHelper::createChecksumAlgorithm(d_.checksumAlgorithm) : 0;
-    std::vector<uint64_t> off, len, sliceLen, sliceSum;
-    std::vector<uint32_t> sliceBase{0};
-    fetched_.clear();
-    // computeShuffleBlocks (:160-197) + S3ShuffleBlockIterator (storage/S3ShuffleBlockIterator.scala:36-43)
-    for (int64_t mapId : mapIds_) {
-      std::vector<int64_t> acc = S3ShuffleHelper::getPartitionLengths(d_, shuffleId_, mapId);
-      if ((int)acc.size() < end_ + 1) throw SparkException("index of map " + std::to_string(mapId) + " has too few partitions");
-      std::vector<int64_t> sums;
-      if (verify) sums = S3ShuffleHelper::getChecksums(d_, shuffleId_, mapId);
-      std::vector<std::pair<int32_t, int32_t>> ranges;
-      if (batch_ && end_ - start_ > 1) ranges.push_back({start_, end_});
-      else for (int32_t r = start_; r < end_; r++) ranges.push_back({r, r + 1});
-      std::ifstream f;
-      for (auto [rs, re] : ranges) {
-        const int64_t a = acc[(size_t)rs], b = acc[(size_t)re];
-        if (b - a == 0) continue;                    // filterNot(_._2.maxBytes == 0)  (:91)
-        remoteBytesRead_ += (uint64_t)(b - a);       // incRemoteBytesRead (:94)
-        Block blk;
-        blk.id = (re - rs > 1) ? BlockId{BlockId::ShuffleBatch, shuffleId_, mapId, rs, re}
-                               : BlockId{BlockId::Shuffle, shuffleId_, mapId, rs, re};
-        blk.srcOff = fetched_.size();
-        blk.srcLen = (uint64_t)(b - a);
-        // S3ShuffleBlockStream: positioned readFully of [acc(start), acc(end)) (storage/S3ShuffleBlockStream.scala:73-92)
-        if (!f.is_open()) {
-          std::string path = d_.getPath(BlockId{BlockId::Data, shuffleId_, mapId, 0, 0});
-          f.open(path, std::ios::binary);
-          if (!f) throw IOException("File does not exist: " + path);
-        }
-        fetched_.resize(blk.srcOff + blk.srcLen);
-        f.seekg(a);
-        f.read((char*)fetched_.data() + blk.srcOff, (std::streamsize)blk.srcLen);
-        if ((uint64_t)f.gcount() != blk.srcLen) throw IOException("short read on " + blk.id.name());
-        off.push_back(blk.srcOff);
-        len.push_back(blk.srcLen);
-        if (verify) {
-          for (int32_t r = rs; r < re; r++) {       // S3ChecksumValidationStream walks .index differences (:68-86)
-            sliceLen.push_back((uint64_t)(acc[(size_t)r + 1] - acc[(size_t)r]));
-            sliceSum.push_back((uint64_t)sums[(size_t)r]);
-          }
-          sliceBase.push_back((uint32_t)sliceLen.size());
-        }
-        blocks_.push_back(blk);
+    std::vector<const uint8_t*> src(n);
+    std::vector<uint64_t> len(n), dlen(n), dcap(n);
+    std::vector<uint32_t> nsl(n);
+    std::vector<const uint64_t*> slen(n), ssum(n);
+    std::vector<std::unique_ptr<uint8_t[]>> spill;  // blocks larger than the task's buffer budget
+    for (uint32_t k = 0; k < n; k++) {
+      auto& st = *got[k].stream;
+      const ShuffleBlockInfo& bi = info_[got[k].tag];
+      src[k] = st.buffered();
+      len[k] = (uint64_t)st.bufferedBytes();
+      if (st.totalBytes() > st.bufferSize()) {  // read the tail through the adaptor, as the JVM codec stream would
+        std::unique_ptr<uint8_t[]> full(new uint8_t[(size_t)st.totalBytes()]);
+        int64_t at = 0, r;
+        while (at < st.totalBytes() && (r = st.read(full.get() + at, st.totalBytes() - at)) > 0) at += r;
+        src[k] = full.get();
+        len[k] = (uint64_t)at;
+        spill.push_back(std::move(full));
       }
+      nsl[k] = (uint32_t)bi.sliceLen.size();
+      slen[k] = bi.sliceLen.data();
+      ssum[k] = bi.sliceSum.data();
     }
-    const uint32_t n = (uint32_t)blocks_.size();
-    if (!n) return;
     ensure_codec_runtime();
     const int codec = d_.codecId();
-    std::vector<uint64_t> doff(n), dlen(n);
     std::vector<int32_t> status(n), bad(n);
-    uint64_t total = 0;
-    if (codec == B2S_CODEC_NONE) {
-      throw UnsupportedOperationException("spark.shuffle.compress=false is served by the stock reader path");
-    }
-    // size pass, then one batch: verify every slice over the compressed bytes, decode, verify block hashes
-    std::vector<const uint8_t*> ptr(n);
-    for (uint32_t k = 0; k < n; k++) ptr[k] = fetched_.data() + off[k];
-    int rc = b2s_decompressed_size_batch((uint32_t)codec, n, ptr.data(), len.data(), dlen.data(), status.data());
+    int rc = b2s_decompressed_size_batch((uint32_t)codec, n, src.data(), len.data(), dlen.data(), status.data());
     if (rc != 0) throw CodecException(std::string("b2s_decompressed_size_batch: ") + b2s_strerror(rc) + ": " + b2s_last_error());
     uint64_t cap = 0;
     for (uint32_t k = 0; k < n; k++) cap += dlen[k];
-    decoded_.resize(cap ? cap : 1);
-    rc = b2s_decompress_packed((uint32_t)codec, alg, n, fetched_.data(), off.data(), len.data(),
-                               verify ? sliceBase.data() : nullptr, verify ? sliceLen.data() : nullptr,
-                               verify ? sliceSum.data() : nullptr, decoded_.data(), cap ? cap : 1, doff.data(),
-                               dlen.data(), &total, status.data(), bad.data());
-    if (rc != 0) throw CodecException(std::string("b2s_decompress_packed: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+    std::unique_ptr<uint8_t[]> out(new uint8_t[(size_t)(cap ? cap : 1)]);
+    std::vector<uint8_t*> dst(n);
+    uint64_t o = 0;
     for (uint32_t k = 0; k < n; k++) {
+      dst[k] = out.get() + o;
+      dcap[k] = dlen[k];
+      o += dlen[k];
+    }
+    rc = b2s_decompress_batch((uint32_t)codec, alg, n, src.data(), len.data(), verify ? nsl.data() : nullptr,
+                              verify ? slen.data() : nullptr, verify ? ssum.data() : nullptr, dst.data(), dcap.data(),
+                              dlen.data(), status.data(), bad.data());
+    for (auto& f : got) f.stream->close();  // onClose(bufferSize): the budget goes back to the prefetcher
+    if (rc != 0) throw CodecException(std::string("b2s_decompress_batch: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+    for (uint32_t k = 0; k < n; k++) {
+      const BlockId& id = info_[got[k].tag].id;
       if (status[k] == B2S_E_CHECKSUM)  // storage/S3ChecksumValidationStream.scala:72-74
-        throw SparkException("Invalid checksum detected for " + blocks_[k].id.name());
+        throw SparkException("Invalid checksum detected for " + id.name());
       if (status[k] == B2S_E_CORRUPT) throw IOException("Stream is corrupted");
       if (status[k] != 0) throw IOException(std::string("decompress failed: ") + b2s_strerror(status[k]));
-      blocks_[k].dstOff = doff[k];
-      blocks_[k].dstLen = dlen[k];
+      Block blk;
+      blk.id = id;
+      blk.data = dst[k];
+      blk.len = dlen[k];
+      blocks_.push_back(blk);
     }
+    decoded_.push_back(std::move(out));
+    batches_++;
+    return true;
   }
   const std::vector<Block>& blocks() const { return blocks_; }
-  const uint8_t* decoded() { return decoded_.data(); }
   uint64_t remoteBytesRead() const { return remoteBytesRead_; }
+  uint64_t remoteBlocksFetched() const { return remoteBlocksFetched_; }
+  uint64_t batches() const { return batches_; }
+  S3BufferedPrefetchIterator::Statistics statistics() { return iter_ ? iter_->statistics() : stats_; }
 
  private:
   S3ShuffleDispatcher& d_;
@@ -572,9 +659,32 @@ class S3ShuffleReader {
   std::vector<int64_t> mapIds_;
   int32_t start_, end_;
   bool batch_;
+  std::vector<ShuffleBlockInfo> info_;
+  std::unique_ptr<S3BufferedPrefetchIterator> iter_;
   std::vector<Block> blocks_;
-  PinnedArena fetched_, decoded_;
-  uint64_t remoteBytesRead_ = 0;
+  std::vector<std::unique_ptr<uint8_t[]>> decoded_;
+  uint64_t remoteBytesRead_ = 0, remoteBlocksFetched_ = 0, batches_ = 0;
+  S3BufferedPrefetchIterator::Statistics stats_;
+};
+
+// the prefetcher on its own (no codec), for the CPU-side tests and for callers that want the compressed blocks
+class PrefetchHandle {
+ public:
+  PrefetchHandle(S3ShuffleDispatcher& d, int32_t shuffleId, const std::vector<int64_t>& mapIds, int32_t start,
+                 int32_t end, bool batch, int64_t maxBufferSize, int maxThreads) {
+    auto src = computeShuffleBlockStreams(d, shuffleId, mapIds, start, end, batch || d.forceBatchFetch, info, remoteBytes,
+                                          remoteBlocks);
+    iter.reset(new S3BufferedPrefetchIterator(std::move(src), maxBufferSize > 0 ? maxBufferSize : d.maxBufferSizeTask,
+                                              maxThreads > 0 ? maxThreads : d.maxConcurrencyTask));
+  }
+  ~PrefetchHandle() {
+    open.clear();   // close the streams the caller still holds before the iterator goes away
+    iter.reset();
+  }
+  std::vector<ShuffleBlockInfo> info;
+  uint64_t remoteBytes = 0, remoteBlocks = 0, nextHandle = 1;
+  std::map<uint64_t, S3BufferedPrefetchIterator::Fetched> open;
+  std::unique_ptr<S3BufferedPrefetchIterator> iter;
 };
 
 }  // namespace host
@@ -589,6 +699,10 @@ static thread_local std::string t_err;
 struct b2sh_dispatcher { std::unique_ptr<S3ShuffleDispatcher> d; };
 struct b2sh_writer { std::unique_ptr<S3ShuffleMapOutputWriter> w; int32_t n; };
 struct b2sh_reader { std::unique_ptr<S3ShuffleReader> r; };
+struct b2sh_prefetch { std::unique_ptr<PrefetchHandle> p; };
+struct b2sh_codec { std::unique_ptr<B200CompressionCodec> c; };
+struct b2sh_ostream { std::unique_ptr<B200CompressedOutputStream> s; };
+struct b2sh_istream { std::unique_ptr<B200CompressedInputStream> s; };
 
 template <typename F>
 static int guarded(F&& f) {
@@ -694,11 +808,133 @@ int b2sh_reader_block(b2sh_reader* r, uint32_t k, int64_t* map_id, int32_t* star
     *map_id = b.id.mapId;
     *start_reduce = b.id.reduceId;
     *end_reduce = b.id.kind == BlockId::ShuffleBatch ? b.id.endReduceId : b.id.reduceId + 1;
-    *data = r->r->decoded() + b.dstOff;
-    *len = b.dstLen;
+    *data = b.data;
+    *len = b.len;
   });
 }
 uint64_t b2sh_reader_remote_bytes_read(b2sh_reader* r) { return r->r->remoteBytesRead(); }
 void b2sh_reader_destroy(b2sh_reader* r) { delete r; }
+
+static void copy_line(const std::string& line, char* buf, uint32_t cap) {
+  if (!buf || !cap) return;
+  const size_t k = std::min<size_t>(line.size(), cap - 1);
+  memcpy(buf, line.data(), k);
+  buf[k] = 0;
+}
+static void fill_prefetch_stats(const S3BufferedPrefetchIterator::Statistics& s, uint64_t* out, char* line, uint32_t cap) {
+  if (out) {
+    out[0] = (uint64_t)s.bytesRead;
+    out[1] = (uint64_t)s.numStreams;
+    out[2] = (uint64_t)s.timeWaiting;
+    out[3] = (uint64_t)s.timePrefetching;
+    out[4] = (uint64_t)s.totalRuntime;
+    out[5] = (uint64_t)s.activeThreads;
+    out[6] = (uint64_t)s.peakMemoryUsage;
+    out[7] = (uint64_t)s.peakThreads;
+  }
+  copy_line(s.line, line, cap);
+}
+
+int b2sh_writer_statistics(b2sh_writer* w, uint64_t* bytes, uint64_t* nanos, char* line, uint32_t cap) {
+  return guarded([&] {
+    const S3MeasureOutputStream* m = w->w->measure();
+    if (!m) throw RuntimeException("no .data object was written");
+    if (bytes) *bytes = (uint64_t)m->bytes();
+    if (nanos) *nanos = (uint64_t)m->timings();
+    copy_line(m->statistics(), line, cap);
+  });
+}
+
+int b2sh_reader_open(b2sh_reader* r) { return guarded([&] { r->r->open(); }); }
+int b2sh_reader_next_batch(b2sh_reader* r, uint32_t max_blocks, uint32_t* n_blocks) {
+  return guarded([&] {
+    const bool more = r->r->nextBatch(max_blocks);
+    *n_blocks = more ? (uint32_t)r->r->blocks().size() : 0;
+  });
+}
+int b2sh_reader_statistics(b2sh_reader* r, uint64_t* out8, uint64_t* batches, char* line, uint32_t cap) {
+  return guarded([&] {
+    fill_prefetch_stats(r->r->statistics(), out8, line, cap);
+    if (batches) *batches = r->r->batches();
+  });
+}
+
+int b2sh_prefetch_create(b2sh_dispatcher* d, int32_t shuffle_id, const int64_t* map_ids, uint32_t n_maps,
+                         int32_t start_partition, int32_t end_partition, int do_batch_fetch, int64_t max_buffer_size,
+                         int32_t max_threads, b2sh_prefetch** out) {
+  return guarded([&] {
+    *out = new b2sh_prefetch{std::make_unique<PrefetchHandle>(*d->d, shuffle_id, std::vector<int64_t>(map_ids, map_ids + n_maps),
+                                                              start_partition, end_partition, do_batch_fetch != 0,
+                                                              max_buffer_size, max_threads)};
+  });
+}
+int b2sh_prefetch_has_next(b2sh_prefetch* p) { return p->p->iter->hasNext() ? 1 : 0; }
+int b2sh_prefetch_next(b2sh_prefetch* p, int64_t* map_id, int32_t* start_reduce, int32_t* end_reduce,
+                       const uint8_t** data, uint64_t* len, uint64_t* stream) {
+  return guarded([&] {
+    S3BufferedPrefetchIterator::Fetched f = p->p->iter->next();
+    *map_id = f.id.mapId;
+    *start_reduce = f.id.reduceId;
+    *end_reduce = f.id.kind == BlockId::ShuffleBatch ? f.id.endReduceId : f.id.reduceId + 1;
+    *data = f.stream->buffered();
+    *len = (uint64_t)f.stream->bufferedBytes();
+    *stream = p->p->nextHandle++;
+    p->p->open.emplace(*stream, std::move(f));
+  });
+}
+int b2sh_prefetch_close_stream(b2sh_prefetch* p, uint64_t stream) {
+  return guarded([&] {
+    auto it = p->p->open.find(stream);
+    if (it == p->p->open.end()) return;  // "Double close detected. Ignoring."
+    it->second.stream->close();
+    p->p->open.erase(it);
+  });
+}
+int b2sh_prefetch_statistics(b2sh_prefetch* p, uint64_t* out8, char* line, uint32_t cap) {
+  return guarded([&] { fill_prefetch_stats(p->p->iter->statistics(), out8, line, cap); });
+}
+void b2sh_prefetch_destroy(b2sh_prefetch* p) { delete p; }
+
+int b2sh_codec_create(b2sh_dispatcher* d, b2sh_codec** out) {
+  return guarded([&] {
+    *out = new b2sh_codec{std::make_unique<B200CompressionCodec>(d->d->codecId(), d->d->lz4BlockSize, d->d->gpuCodecBufferSize)};
+  });
+}
+int b2sh_codec_supports_concatenation(b2sh_codec* c) {
+  return B200CompressionCodec::supportsConcatenationOfSerializedStreams(c->c->codecId()) ? 1 : 0;
+}
+void b2sh_codec_destroy(b2sh_codec* c) { delete c; }
+int b2sh_codec_output_stream(b2sh_codec* c, b2sh_sink_fn sink, void* ctx, b2sh_ostream** out) {
+  return guarded([&] {
+    if (!sink) throw RuntimeException("sink is null");
+    *out = new b2sh_ostream{std::make_unique<B200CompressedOutputStream>(*c->c, [sink, ctx](const uint8_t* b, uint64_t n) {
+      if (sink(ctx, b, n) < 0) throw IOException("the sink rejected the write");
+    })};
+  });
+}
+int b2sh_ostream_write(b2sh_ostream* s, const uint8_t* bytes, uint64_t n) { return guarded([&] { s->s->write(bytes, n); }); }
+int b2sh_ostream_flush(b2sh_ostream* s) { return guarded([&] { s->s->flush(); }); }
+int b2sh_ostream_close(b2sh_ostream* s, uint64_t* bytes_in, uint64_t* bytes_out, uint32_t* streams) {
+  return guarded([&] {
+    s->s->close();
+    if (bytes_in) *bytes_in = s->s->bytesIn();
+    if (bytes_out) *bytes_out = s->s->bytesOut();
+    if (streams) *streams = s->s->streamsEmitted();
+  });
+}
+void b2sh_ostream_destroy(b2sh_ostream* s) { delete s; }
+int b2sh_codec_input_stream(b2sh_codec* c, b2sh_source_fn source, void* ctx, b2sh_istream** out) {
+  return guarded([&] {
+    if (!source) throw RuntimeException("source is null");
+    *out = new b2sh_istream{std::make_unique<B200CompressedInputStream>(*c->c, [source, ctx](uint8_t* b, uint64_t cap) {
+      return source(ctx, b, cap);
+    })};
+  });
+}
+int b2sh_istream_read(b2sh_istream* s, uint8_t* buf, uint64_t cap, int64_t* got) {
+  return guarded([&] { *got = s->s->read(buf, cap); });
+}
+int b2sh_istream_close(b2sh_istream* s) { return guarded([&] { s->s->close(); }); }
+void b2sh_istream_destroy(b2sh_istream* s) { delete s; }
 
 }  // extern "C"
