@@ -106,6 +106,7 @@ def cpu_arm(oracle, sample, block_bytes, threads, repeats=1):
 
 
 def main():
+    global RECORDS_PER_BLOCK
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -113,6 +114,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=int(os.environ.get("B2S_BENCH_BLOCKS", N_BLOCKS_FULL)),
                     help="shuffle blocks per GPU (16000 = the 10 GiB config; smaller only for quick checks)")
+    ap.add_argument("--records-per-block", type=int, default=RECORDS_PER_BLOCK,
+                    help="104-byte records per shuffle block: 6453 = config 2 (default), 630 = config 3's ~64 KiB blocks")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-blocks", type=int, default=6000)
     ap.add_argument("--no-e2e", action="store_true")
@@ -126,10 +129,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     steps, warmup = args.steps, max(args.warmup, 3)
     n = args.blocks
+    RECORDS_PER_BLOCK = args.records_per_block
     block_bytes = RECORDS_PER_BLOCK * RECORD
     total = n * block_bytes
-    workload = "terasort %.2f GiB/GPU, %d shuffle blocks x %d B (80 maps x 200 partitions), LZ4Block 32 KiB + CRC32C" % (
-        total / 2**30, n, block_bytes)
+    workload = "terasort %.2f GiB/GPU, %d shuffle blocks x %d B (%s), LZ4Block 32 KiB + CRC32C" % (
+        total / 2**30, n, block_bytes,
+        "80 maps x 200 partitions" if RECORDS_PER_BLOCK == 6453 else "config-3 shape: 2 full LZ4 blocks + end mark per block")
     codec_desc = {"lz4": "lz4 (LZ4Block, blockSize 32 KiB)", "snappy": "snappy (xerial framing, blockSize 32 KiB)",
                   "zstd": "zstd (frames of 32 KiB blocks; raw literals + predefined-FSE sequences)"}[args.codec]
     if args.codec != "lz4":

@@ -129,7 +129,7 @@ struct Slot {
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;            // kernel region
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;            // dominant kernel
   cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;  // copies
-  DevBuf meta, scratch, desc, src, dst;
+  DevBuf meta, scratch, desc, src, dst, zmeta;
   PinBuf hmeta;
   // per-launch event pairs around the dominant kernel of a call (grow-only pool; `used` pairs are valid)
   std::vector<cudaEvent_t> ev_dom;
@@ -387,6 +387,10 @@ struct DecompressJob {
            *work_base = nullptr, *ws = nullptr;
   int32_t *status = nullptr, *bad = nullptr;
   unsigned int* counter = nullptr;
+  // zstd: per-stream counts / bases (blocks, sequences, literal bytes) and their totals
+  uint64_t *zcnt = nullptr, *zbase = nullptr;
+  uint64_t znb = 0, znseq = 0, zlit = 0;
+  bool size_only = false;
 };
 
 int decompress_prepare(Slot& S, uint32_t codec, uint32_t alg, uint32_t n, uint32_t n_slices, DecompressJob& J) {
@@ -466,11 +470,34 @@ int decompress_enqueue_a(Slot& S, const ChecksumTables& tabs, uint32_t alg, Deco
     launch_checksum_compare(J.cks_got, J.slice_sum, J.slice_owner, J.slice_base, s, J.status, J.bad, st, launches);
   }
   if (J.codec == B2S_CODEC_ZSTD) {
-    // no per-block descriptors: a frame is a serial unit; the size pass runs the sequence decoder without copying
-    rc = S.scratch.ensure(zstd_ws_bytes(n));
+    // walk (count) -> totals to the host -> walk (fill) -> entropy decode of every block in parallel -> stream sizes.
+    // The one blocking readback sizes the descriptor array and the literal / sequence workspace (zstd_par.h).
+    rc = S.zmeta.ensure(((size_t)n * 6 + 8) * 8);
     if (rc) return rc;
+    J.zcnt = (uint64_t*)S.zmeta.p;
+    J.zbase = J.zcnt + (size_t)n * 3;
+    uint64_t* ztot = J.zbase + (size_t)n * 3;
+    launch_zstd_count(d_src, J.src_off, J.src_len, n, J.zcnt, J.status, st, launches);
+    CU(cudaMemcpyAsync(J.zbase, J.zcnt, (size_t)n * 24, cudaMemcpyDeviceToDevice, st));
+    for (int k = 0; k < 3; k++) launch_exclusive_scan_u64(J.zbase + (size_t)n * k, n, ztot + k, J.ws, st, launches);
+    uint64_t h[3] = {0, 0, 0};
+    CU(cudaMemcpyAsync(h, ztot, 24, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    J.znb = h[0];
+    J.znseq = h[1];
+    J.zlit = h[2];
+    if (J.znb >= 0x7fffffffull) return fail(B2S_E_ARG, "too many Zstandard blocks in one chunk%s");
+    rc = S.desc.ensure((size_t)(J.znb + 1) * zstd_block_info_bytes());
+    if (rc) return rc;
+    if (!J.size_only) {
+      rc = S.scratch.ensure(zstd_ws_bytes(J.zlit, J.znseq));
+      if (rc) return rc;
+    }
+    launch_zstd_fill(d_src, J.src_off, J.src_len, n, J.zcnt, J.zbase, S.desc.p, J.status, st, launches);
+    launch_zstd_entropy(J.size_only, d_src, S.desc.p, J.znb, (uint8_t*)S.scratch.p, J.zlit, J.znseq, J.status, st,
+                        launches);
+    launch_zstd_sum(S.desc.p, J.zcnt, J.zbase, n, J.olen, J.status, st, launches);
     CU(cudaMemsetAsync(J.nblk, 0, (size_t)n * 8, st));
-    launch_zstd_sizes(d_src, J.src_off, J.src_len, n, (uint8_t*)S.scratch.p, J.olen, J.status, st, launches);
   } else if (J.codec == B2S_CODEC_SNAPPY_XERIAL)
     launch_xerial_count(d_src, J.src_off, J.src_len, n, J.nblk, J.olen, J.totals + 2, J.status, st, launches);
   else
@@ -493,8 +520,8 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
   if (J.codec == B2S_CODEC_ZSTD) {
     cudaStream_t zst = S.st;
     CU(cudaEventRecord(S.ev_t0, zst));
-    launch_zstd_decode(d_src, J.src_off, J.src_len, J.n, (uint8_t*)S.scratch.p, J.olen, d_dst, J.dst_off, dst_cap,
-                       J.status, zst, launches);
+    launch_zstd_execute(d_src, S.desc.p, J.zcnt, J.zbase, J.n, (const uint8_t*)S.scratch.p, J.zlit, J.znseq, J.olen,
+                        d_dst, J.dst_off, dst_cap, J.status, zst, launches);
     CU(cudaEventRecord(S.ev_t1, zst));
     CU(cudaEventRecord(S.ev_k1, zst));
     CU(cudaMemcpyAsync(J.h_down, J.d_down, J.down_bytes, cudaMemcpyDeviceToHost, zst));
@@ -784,6 +811,7 @@ void b2s_shutdown(void) {
       S.meta.release();
       S.scratch.release();
       S.desc.release();
+      S.zmeta.release();
       S.src.release();
       S.dst.release();
       S.hmeta.release();
@@ -1370,6 +1398,7 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
     const uint32_t ns = alg ? slice_base[i0 + cnt] - slice_base[i0] : 0;
     int r = decompress_prepare(S, codec, alg, cnt, ns, J);
     if (r) return r;
+    J.size_only = size_only;
     memcpy(J.h_src_len, src_len + i0, (size_t)cnt * 8);
     uint64_t bytes = plan_runs(cnt, src + i0, src_len + i0, J.h_src_off, runs[c % NSLOT]);
     chunk_src_bytes[c] = bytes;

@@ -112,15 +112,26 @@ void launch_snappy_tokens(const BlockDesc* d_desc, uint32_t b0, uint32_t m, cons
                           uint32_t rec_stride, uint32_t* d_nrec, int32_t* d_status, cudaStream_t st,
                           uint64_t* launches);
 
-// ---------------- zstd.cu (K6: Zstandard frame decoding, thread per stream; core in zstd_core.h) ----------------
-size_t zstd_ws_bytes(uint32_t n_streams);
-// decoded size of every stream (status CORRUPT / UNSUPPORTED on malformed input; streams with status != 0 are skipped)
-void launch_zstd_sizes(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
-                       uint8_t* d_ws, uint64_t* d_olen, int32_t* d_status, cudaStream_t st, uint64_t* launches);
-// decodes stream i to dst_base + d_dst_off[i] (d_olen[i] bytes, as computed by launch_zstd_sizes)
-void launch_zstd_decode(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
-                        uint8_t* d_ws, uint64_t* d_olen, uint8_t* dst_base, const uint64_t* d_dst_off, uint64_t dst_cap,
-                        int32_t* d_status, cudaStream_t st, uint64_t* launches);
+// ---------------- zstd.cu (K6: Zstandard frame decoding, block-parallel; core in zstd_core.h + zstd_par.h) ----------------
+// d_cnt / d_base: three arrays of n u64 each (blocks, sequences, literal-workspace bytes per stream); d_base holds their
+// exclusive scans.  d_blocks: zstd_block_info_bytes() per block.  d_ws: zstd_ws_bytes(total literals, total sequences).
+size_t zstd_block_info_bytes();
+size_t zstd_ws_bytes(uint64_t lit_bytes, uint64_t nseq);
+void launch_zstd_count(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
+                       uint64_t* d_cnt, int32_t* d_status, cudaStream_t st, uint64_t* launches);
+void launch_zstd_fill(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len, uint32_t n,
+                      uint64_t* d_cnt, const uint64_t* d_base, void* d_blocks, int32_t* d_status, cudaStream_t st,
+                      uint64_t* launches);
+// warp per block: literals + sequences into d_ws (size_only: nothing stored), block sizes into d_blocks
+void launch_zstd_entropy(bool size_only, const uint8_t* src_base, void* d_blocks, uint64_t nb, uint8_t* d_ws,
+                         uint64_t lit_bytes, uint64_t nseq, int32_t* d_status, cudaStream_t st, uint64_t* launches);
+void launch_zstd_sum(const void* d_blocks, const uint64_t* d_cnt, const uint64_t* d_base, uint32_t n, uint64_t* d_olen,
+                     const int32_t* d_status, cudaStream_t st, uint64_t* launches);
+// warp per stream: decodes stream i to dst_base + d_dst_off[i] (d_olen[i] bytes, as computed by launch_zstd_sum)
+void launch_zstd_execute(const uint8_t* src_base, const void* d_blocks, const uint64_t* d_cnt, const uint64_t* d_base,
+                         uint32_t n, const uint8_t* d_ws, uint64_t lit_bytes, uint64_t nseq, const uint64_t* d_olen,
+                         uint8_t* dst_base, const uint64_t* d_dst_off, uint64_t dst_cap, int32_t* d_status,
+                         cudaStream_t st, uint64_t* launches);
 
 // ---------------- zstd_enc.cu (K7: Zstandard frame encoding: raw literals + predefined-FSE sequences) ----------------
 int zstd_ctables_create(void** d_tables);  // predefined FSE compression tables, on the current device

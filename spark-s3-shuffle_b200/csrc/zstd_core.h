@@ -25,7 +25,9 @@
 // Cooperative execution.  On the device the decoder runs with ALL 32 lanes of a warp executing the same control flow on
 // the same data (the serial parts are simply computed redundantly, which costs a warp no more than one lane would),
 // so that the byte-copy loops can be split across the lanes and the four Huffman streams of a literals section across
-// four lanes.  zstd.cu defines B2S_ZSTD_WARP before including this header; everywhere else one "lane" does everything.
+// four lanes (zstd_par.h, the block-parallel decomposition the kernels run).  zstd.cu defines B2S_ZSTD_WARP before
+// including this header; everywhere else one "lane" does everything.  decode_stream() below is the single-pass
+// statement of the format, kept as the reference the decomposition is tested against on the host.
 #if defined(B2S_ZSTD_WARP) && defined(__CUDA_ARCH__)
 #define B2S_LANE ((int)(threadIdx.x & 31))
 #define B2S_NLANES 32
@@ -53,10 +55,27 @@ struct FseEntry {
 
 // per-stream decoder state: ~11 KB of tables (shared memory on the device) + a pointer to the literals buffer
 struct Workspace {
+#ifdef B2S_ZSTD_UNION_TABLES
+  // Block-parallel decoding (zstd_par.h) rebuilds every table per block and is done with the literals before it
+  // starts on the sequences, so the Huffman tables and the three sequence tables can share their bytes: 6.6 KB instead
+  // of 11 KB per warp, i.e. 32 instead of 20 resident warps per SM.  (decode_stream keeps tables across blocks and
+  // must not be built this way.)
+  union {
+    struct {
+      FseEntry ll[512], of[256], ml[512];
+    };
+    struct {
+      uint16_t huf[2048];  // Huffman decoding table: symbol | nbits << 8, 2^maxbits entries (maxbits <= 11)
+      FseEntry wt[64];     // Huffman weights (FSE, accuracy <= 6)
+      uint8_t weights[256];
+    };
+  };
+#else
   FseEntry ll[512], of[256], ml[512];
   FseEntry wt[64];        // Huffman weights (FSE, accuracy <= 6)
   uint16_t huf[2048];     // Huffman decoding table: symbol | nbits << 8, 2^maxbits entries (maxbits <= 11)
   uint8_t weights[256];
+#endif
   uint8_t* lit;           // kBlockMax + 64 bytes (global memory on the device; the tables above sit in shared memory)
   int16_t norm[64];
   uint16_t next[64];
@@ -470,23 +489,10 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
         const uint64_t q = (regen + 3) / 4;
         if (3 * q > regen) return kErrCorrupt;
         const uint8_t* a = ls + 6;
-#if defined(B2S_ZSTD_WARP) && defined(__CUDA_ARCH__)
-        {  // one lane per stream; every lane needs the verdict
-          bool ok = true;
-          const int l = B2S_LANE;
-          if (l == 0) ok = huf_decode_stream(w, a, s1, w->lit, q);
-          else if (l == 1) ok = huf_decode_stream(w, a + s1, s2, w->lit + q, q);
-          else if (l == 2) ok = huf_decode_stream(w, a + s1 + s2, s3, w->lit + 2 * q, q);
-          else if (l == 3) ok = huf_decode_stream(w, a + s1 + s2 + s3, s4, w->lit + 3 * q, regen - 3 * q);
-          B2S_SYNC();
-          if (!B2S_ALL(ok)) return kErrCorrupt;
-        }
-#else
         if (!huf_decode_stream(w, a, s1, w->lit, q)) return kErrCorrupt;
         if (!huf_decode_stream(w, a + s1, s2, w->lit + q, q)) return kErrCorrupt;
         if (!huf_decode_stream(w, a + s1 + s2, s3, w->lit + 2 * q, q)) return kErrCorrupt;
         if (!huf_decode_stream(w, a + s1 + s2 + s3, s4, w->lit + 3 * q, regen - 3 * q)) return kErrCorrupt;
-#endif
       }
     }
     lit = w->lit;
@@ -521,9 +527,6 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
     BitsRev br;
     if (ip >= n || !br.init(src + ip, n - ip)) return kErrCorrupt;
     uint32_t sl = br.read(w->ll_log), so = br.read(w->of_log), sm = br.read(w->ml_log);
-#if defined(B2S_ZSTD_WARP) && defined(__CUDA_ARCH__)
-    int my_ll = 0, my_ml = 0, my_off = 0, my_lpos = 0, my_o = 0, nb = 0;
-#endif
     for (uint32_t i = 0; i < nseq; i++) {
       const int oc = w->of[so].sym, mc = w->ml[sm].sym, lc = w->ll[sl].sym;
       if (oc > 31 || mc > 52 || lc > 35) return kErrCorrupt;
@@ -561,41 +564,10 @@ B2S_HD inline int64_t decode_compressed_block(Workspace* w, const uint8_t* src, 
         const uint64_t o = op + produced;
         if (o + llen + mlen > cap) return kErrDstTooSmall;
         if ((uint64_t)offset > o + llen) return kErrCorrupt;  // reaches before the start of the frame
-#if defined(B2S_ZSTD_WARP) && defined(__CUDA_ARCH__)
-        // warp build: lane `nb` latches this sequence; 32 of them are then executed together (below)
-        if (B2S_LANE == nb) {
-          my_ll = (int)llen;
-          my_ml = (int)mlen;
-          my_off = (int)offset;
-          my_lpos = (int)lpos;
-          my_o = (int)produced;
-        } else if (B2S_LANE > nb) {  // not latched yet: sit (empty) at the end of what has been decoded
-          my_ll = my_ml = 0;
-          my_o = (int)(produced + llen + mlen);
-        }
-        nb++;
-        if (nb == 32 || i + 1 == nseq) {
-          uint8_t* ob = out + op;  // block base: positions inside the block fit an int, earlier output is final
-          if (my_ll <= 32)
-            for (int k = 0; k < my_ll; k++) ob[my_o + k] = lit[my_lpos + k];
-          unsigned big = __ballot_sync(0xffffffffu, my_ll > 32);
-          while (big) {
-            const int l = __ffs(big) - 1;
-            big &= big - 1;
-            const int n_l = __shfl_sync(0xffffffffu, my_ll, l), o_l = __shfl_sync(0xffffffffu, my_o, l),
-                      p_l = __shfl_sync(0xffffffffu, my_lpos, l);
-            for (int k = B2S_LANE; k < n_l; k += 32) ob[o_l + k] = lit[p_l + k];
-          }
-          __syncwarp();
-          lz_execute_matches(ob, my_o + my_ll, my_ml, my_off, B2S_LANE);
-          nb = 0;
-        }
-#else
         for (uint32_t k = 0; k < llen; k++) out[o + k] = lit[lpos + k];
         uint8_t* d = out + o + llen;
         const uint8_t* s = d - offset;
         for (uint32_t k = 0; k < mlen; k++) d[k] = s[k];
-#endif
       }
       lpos += llen;
       produced += (uint64_t)llen + mlen;

@@ -25,6 +25,40 @@ long long zc_size(const unsigned char* src, unsigned long long n) {
 unsigned long long zc_workspace_bytes() { return sizeof(b2s::zstd::Workspace); }
 }
 
+// the block-parallel decomposition (zstd_par.h): walk (count, fill) -> entropy per block -> execute, run one after the
+// other exactly as the three kernels of zstd.cu do
+#include <vector>
+
+#include "../../spark-s3-shuffle_b200/csrc/zstd_par.h"
+extern "C" long long zc_decode_par(const unsigned char* src, unsigned long long n, unsigned char* dst,
+                                   unsigned long long cap, int size_only) {
+  using namespace b2s::zstd;
+  StreamTotals t{0, 0, 0};
+  int rc = walk_stream(src, n, nullptr, 0, 0, 0, 0, 0, &t);
+  if (rc < 0) return rc;
+  std::vector<BlockInfo> blocks(t.nblk ? t.nblk : 1);
+  StreamTotals t2{0, 0, 0};
+  rc = walk_stream(src, n, blocks.data(), 0, 0, 0, 0, 0, &t2);
+  if (rc < 0 || t2.nblk != t.nblk || t2.nseq != t.nseq || t2.lit != t.lit) return -100;
+  std::vector<unsigned char> lit(t.lit + 64);
+  std::vector<uint32_t> ll(t.nseq + 1), ml(t.nseq + 1), ofv(t.nseq + 1);
+  Workspace* w = (Workspace*)malloc(sizeof(Workspace));
+  w->lit = nullptr;
+  long long total = 0;
+  for (uint32_t b = 0; b < t.nblk; b++) {
+    const long long r = entropy_block(w, blocks.data(), b, src, lit.data(), ll.data(), ml.data(), ofv.data(), size_only != 0);
+    if (r < 0) {
+      free(w);
+      return r;
+    }
+    blocks[b].out_size = (uint32_t)r;
+    total += r;
+  }
+  free(w);
+  if (size_only) return total;
+  return execute_stream(blocks.data(), (uint32_t)t.nblk, src, lit.data(), ll.data(), ml.data(), ofv.data(), dst, cap);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // CPU model of the GPU Zstandard ENCODER (zstd_enc.cu): the shared window match finder + greedy parse (the same
 // specification as orc_lz4_compress_block_win in oracle/), then the encoder core of zstd_enc_core.h.

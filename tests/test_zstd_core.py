@@ -23,12 +23,33 @@ def zc(tmp_path_factory):
     L.zc_decode.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong]
     L.zc_size.restype = C.c_longlong
     L.zc_size.argtypes = [C.c_char_p, C.c_ulonglong]
+    L.zc_decode_par.restype = C.c_longlong
+    L.zc_decode_par.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_int]
+    single_pass_size = L.zc_size
+
+    def size_both(frame, n):
+        """size pass of the single-pass decoder and of the block-parallel decomposition must agree"""
+        a = single_pass_size(frame, n)
+        b = L.zc_decode_par(frame, n, None, 0, 1)
+        assert (a < 0 and b < 0) or a == b, (a, b)
+        return a
+
+    L.zc_size = size_both
     return L
 
 
 def decode(zc, frame, cap):
+    """every frame goes through BOTH statements of the decoder — decode_stream (single pass, zstd_core.h) and
+    walk -> entropy -> execute (block-parallel, zstd_par.h); they must agree"""
     out = C.create_string_buffer(max(cap, 1))
     r = zc.zc_decode(frame, len(frame), out, cap)
+    out2 = C.create_string_buffer(max(cap, 1))
+    r2 = zc.zc_decode_par(frame, len(frame), out2, cap, 0)
+    assert (r < 0 and r2 < 0) or r == r2, (r, r2)
+    if r >= 0:
+        assert out.raw[:r] == out2.raw[:r2]
+    if r == -3:
+        assert r2 == -3
     return r, out.raw[:max(r, 0)]
 
 
@@ -112,3 +133,22 @@ def test_encoder_model_frames_are_read_by_libzstd(zc, oracle):
                 r, out = decode(zc, f, n)
                 assert r == n and out == d
     assert zc.zc_compress_model(b"", 0, 32768, buf, cap) == 9   # frame header + empty last block
+
+
+def test_block_parallel_decoder_with_shared_table_storage(tmp_path, oracle):
+    """the device build of zstd_par.h overlays the Huffman and the sequence tables (B2S_ZSTD_UNION_TABLES): same frames,
+    same answers"""
+    out = str(tmp_path / "libzcu.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DB2S_ZSTD_UNION_TABLES", "-o", out,
+                           os.path.join(ROOT, "tests", "native", "zstd_core_host.cpp")])
+    L = C.CDLL(out)
+    L.zc_decode_par.restype = C.c_longlong
+    L.zc_decode_par.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_int]
+    assert L.zc_workspace_bytes() < 7000
+    for kind in ("terasort", "text", "ints", "runs"):
+        for n in (0, 777, 40000, 500000):
+            d = corpus(oracle, kind, n, seed=11)
+            for f in (zstd_ref.compress(d, 3), zstd_ref.compress_stream(d, 1, 32768, 3), zstd_ref.compress_stream(d, 3)):
+                buf = C.create_string_buffer(max(n, 1))
+                assert L.zc_decode_par(f, len(f), buf, n, 0) == n and buf.raw[:n] == d
+                assert L.zc_decode_par(f, len(f), None, 0, 1) == n
