@@ -85,6 +85,9 @@ struct Workspace {
 };
 
 B2S_HD inline int highbit32(uint32_t v) {  // position of the highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz((int)v);
+#endif
   int r = 0;
   while (v >>= 1) r++;
   return r;
@@ -109,25 +112,38 @@ struct BitsFwd {
 // when the cursor leaves it) so a read is a shift and a mask, not a fresh walk over memory.
 struct BitsRev {
   const uint8_t* p;
-  int64_t n;
-  int64_t pos;  // bits still unread; may go negative (over-read: zeros), checked by the callers
+  int32_t n;    // bytes (a literals stream or a sequence bitstream is at most one block: < 2^17 bytes, 2^20 bits)
+  int32_t pos;  // bits still unread; may go negative (over-read: zeros), checked by the callers
   uint64_t buf;
-  int64_t lo;   // bit index of buf's bit 0 (multiple of 8; may be negative: bits below the stream start are zero)
-  B2S_HD void fill(int64_t want_lo) {  // buf := stream bits [want_lo, want_lo + 64)
+  int32_t lo;   // bit index of buf's bit 0 (multiple of 8; may be negative: bits below the stream start are zero)
+  B2S_HD void fill(int32_t want_lo) {  // buf := stream bits [want_lo, want_lo + 64)
     lo = want_lo;
     uint64_t v = 0;
-    const int64_t b = want_lo >> 3;  // arithmetic shift: negative byte indices read as zero
+    const int32_t b = want_lo >> 3;  // arithmetic shift: negative byte indices read as zero
+    if (b >= 0 && b + 16 <= n) {     // away from both ends: two aligned 8-byte loads instead of eight byte loads
+#ifdef __CUDA_ARCH__
+      const uintptr_t a = reinterpret_cast<uintptr_t>(p + b);
+      const uint64_t* wp = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
+      const unsigned sh = (unsigned)(a & 7u) * 8u;
+      const uint64_t x0 = wp[0], x1 = wp[1];  // wp[1] ends at most 15 bytes after p + b: inside the stream
+      buf = sh ? (x0 >> sh) | (x1 << (64u - sh)) : x0;
+#else
+      for (int i = 0; i < 8; i++) v |= (uint64_t)p[b + i] << (8 * i);
+      buf = v;
+#endif
+      return;
+    }
     for (int i = 0; i < 8; i++) {
-      const int64_t k = b + i;
+      const int32_t k = b + i;
       if (k >= 0 && k < n) v |= (uint64_t)p[k] << (8 * i);
     }
     buf = v;
   }
   B2S_HD bool init(const uint8_t* src, uint64_t len) {
     p = src;
-    n = (int64_t)len;
-    if (len == 0 || src[len - 1] == 0) return false;
-    pos = (int64_t)(len - 1) * 8 + highbit32(src[len - 1]);
+    if (len == 0 || len > (1u << 24) || src[len - 1] == 0) return false;
+    n = (int32_t)len;
+    pos = (int32_t)(len - 1) * 8 + highbit32(src[len - 1]);
     fill(((pos - 57) >> 3) * 8);  // pos lies within the top byte of the buffer
     return true;
   }
@@ -135,7 +151,7 @@ struct BitsRev {
     if (nb == 0) return 0;
     pos -= nb;
     if (pos < lo) fill(((pos - 24) >> 3) * 8);  // keep >= 32 bits above pos available: pos - lo in [24, 31]
-    return (uint32_t)((buf >> (pos - lo)) & ((1ull << nb) - 1));
+    return (uint32_t)(buf >> (pos - lo)) & (0xffffffffu >> (32 - nb));
   }
 };
 
@@ -318,7 +334,7 @@ B2S_HD inline bool huf_decode_stream(const Workspace* w, const uint8_t* src, uin
     state = ((state << nb) & mask) | br.read(nb);
   }
   // every stream must be consumed exactly: the over-read equals the initial state's width
-  return br.pos == -(int64_t)mb;
+  return br.pos == -mb;
 }
 
 // ---- sequences ---------------------------------------------------------------------------------------------------

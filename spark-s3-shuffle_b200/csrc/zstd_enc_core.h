@@ -157,8 +157,8 @@ B2S_HD inline void ml_encode(uint32_t ml, int* code, int* nbits, uint32_t* extra
 
 // ---- forward bit writer (the sequence bitstream is written forwards, sequences in reverse order) ------------------
 struct BitWriter {
-  uint8_t* p;
-  uint32_t cap, n;  // bytes written so far; overflow => n stays > cap
+  uint8_t* p;       // 4-byte aligned, with at least 8 bytes of slack beyond `cap`
+  uint32_t cap, n;  // bytes written so far; overflow => n ends > cap (nothing is stored past cap + 4)
   uint64_t acc;
   int fill;
   B2S_HD void init(uint8_t* dst, uint32_t capacity) {
@@ -168,23 +168,33 @@ struct BitWriter {
     acc = 0;
     fill = 0;
   }
-  B2S_HD void add(uint32_t v, int nb) {  // nb <= 24 per call
+  // Flushes 32 bits at a time with one aligned word store.  (The first version flushed byte by byte in a loop whose
+  // trip count differed between the 32 blocks a warp encodes: ~900 warp-instructions per sequence, profiles/r1z.)
+  B2S_HD void add(uint32_t v, int nb) {  // nb <= 24 per call, fill < 32 on entry
     acc |= (uint64_t)(v & ((1u << nb) - 1u)) << fill;
     fill += nb;
-    while (fill >= 8) {
-      if (n < cap) p[n] = (uint8_t)acc;
+    if (fill >= 32) {
+      if (n <= cap) {
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint32_t*>(p + n) = (uint32_t)acc;
+#else
+        for (int k = 0; k < 4; k++) p[n + k] = (uint8_t)(acc >> (8 * k));
+#endif
+      }
+      n += 4;
+      acc >>= 32;
+      fill -= 32;
+    }
+  }
+  B2S_HD void close() {  // final 1-bit marker, then the last partial word byte by byte
+    add(1, 1);
+    while (fill > 0) {
+      if (n <= cap) p[n] = (uint8_t)acc;
       n++;
       acc >>= 8;
       fill -= 8;
     }
-  }
-  B2S_HD void close() {  // final 1-bit marker
-    add(1, 1);
-    if (fill) {
-      if (n < cap) p[n] = (uint8_t)acc;
-      n++;
-      fill = 0;
-    }
+    fill = 0;
   }
 };
 

@@ -327,7 +327,7 @@ B2S_HD inline int64_t entropy_block(Workspace* w, const BlockInfo* blocks, uint3
     }
   }
   // ---- sequences
-  uint64_t produced = 0, lpos = 0;
+  uint32_t produced = 0, lpos = 0;  // both <= kBlockMax
   if (b.nseq) {
     uint64_t ip = (uint64_t)b.seq_off + 1;  // past the modes byte
     for (int kind = 0; kind < 3; kind++) {
@@ -364,7 +364,7 @@ B2S_HD inline int64_t entropy_block(Workspace* w, const BlockInfo* blocks, uint3
       if (lpos + llen > b.regen) return kErrCorrupt;
       if (produced + llen + mlen > kBlockMax) return kErrCorrupt;
       lpos += llen;
-      produced += (uint64_t)llen + mlen;
+      produced += llen + mlen;
       if (!size_only) {  // lane (i mod NLANES) latches the triple; stored NLANES at a time (coalesced on the device)
         if (B2S_LANE == nb) {
           my_ll = llen;
@@ -390,7 +390,7 @@ B2S_HD inline int64_t entropy_block(Workspace* w, const BlockInfo* blocks, uint3
     }
     if (br.pos != 0) return kErrCorrupt;
   }
-  const uint64_t total = produced + (b.regen - lpos);
+  const uint32_t total = produced + (b.regen - lpos);
   if (total > kBlockMax) return kErrCorrupt;
   return (int64_t)total;
 }
