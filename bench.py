@@ -91,11 +91,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+CPU_CODEC = "lz4"  # set from --codec
+CPU_NOTES = {
+    "lz4": "oracle framing/XXH32/CRC32C + liblz4.so.1 LZ4_compress_default/LZ4_decompress_fast (the native routines "
+           "lz4-java's JNI path calls); no JVM stream wrappers / JNI => upper bound on the reference",
+    "snappy": "oracle xerial framing + restated raw-Snappy compressor/decompressor + CRC32C (snappy-java's native side is "
+              "absent here); no JVM stream wrappers / JNI",
+    "zstd": "libzstd.so.1 ZSTD_compress level 3 / ZSTD_decompress (what zstd-jni executes; BASELINE config 5's level) + "
+            "CRC32C; no JVM stream wrappers / JNI => upper bound on the reference",
+}
+
+
 def cpu_arm(oracle, sample, block_bytes, threads, repeats=1):
     """reference CPU arithmetic on `sample` (numpy uint8): returns (GB/s write+read, detail)"""
     best = None
     for _ in range(repeats):
-        r = oracle.baseline_run(sample, block_bytes, LZ4_BLOCK, oracle.CRC32C, threads=threads, use_liblz4=True)
+        r = oracle.baseline_run_codec(CPU_CODEC, sample, block_bytes, LZ4_BLOCK, oracle.CRC32C, threads=threads, level=3)
         if r["rc"] != 0:
             raise RuntimeError("CPU baseline reported %d errors" % r["errors"])
         t = r["write_s"] + r["read_s"]
@@ -106,7 +117,7 @@ def cpu_arm(oracle, sample, block_bytes, threads, repeats=1):
 
 
 def main():
-    global RECORDS_PER_BLOCK
+    global RECORDS_PER_BLOCK, CPU_CODEC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -130,6 +141,7 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3)
     n = args.blocks
     RECORDS_PER_BLOCK = args.records_per_block
+    CPU_CODEC = args.codec
     block_bytes = RECORDS_PER_BLOCK * RECORD
     total = n * block_bytes
     workload = "terasort %.2f GiB/GPU, %d shuffle blocks x %d B (%s), LZ4Block 32 KiB + CRC32C" % (
@@ -166,8 +178,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": threads,
                                  "kind": "port", "sample": sample_desc,
-                                 "note": "oracle framing/XXH32/CRC32C + liblz4.so.1 LZ4_compress_default/LZ4_decompress_fast "
-                                         "(the native routines lz4-java's JNI path calls); no JVM wrappers => upper bound on the reference",
+                                 "note": CPU_NOTES[args.codec],
                                  "compressed_ratio": round(detail["compressed_bytes"] / detail["bytes"], 4)},
                 "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -339,7 +350,7 @@ def main():
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and args.codec == "lz4":
+    if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         sample_blocks = min(args.cpu_sample_blocks, n)
         sample = oracle.gen_terasort(0, sample_blocks * RECORDS_PER_BLOCK)
@@ -350,8 +361,7 @@ def main():
                "sample": "%d of %d shuffle blocks (%.2f GiB), same generator/seed, best of 2" % (
                    sample_blocks, n, sample.size / 2**30),
                "single_core_GBps": round(v1, 3),
-               "note": "oracle framing/XXH32/CRC32C + liblz4.so.1 LZ4_compress_default/LZ4_decompress_fast; "
-                       "native proxy of the JVM path (no stream wrappers / JNI) => upper bound on the reference"}
+               "note": CPU_NOTES[args.codec]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": steps,

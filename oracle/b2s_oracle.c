@@ -799,6 +799,7 @@ typedef struct {
   uint32_t* sums;
   int phase;
   int errors;
+  const orc_codec_job* cj; /* NULL: LZ4Block */
 } bl_worker;
 
 static double now_s(void) {
@@ -814,10 +815,21 @@ static void* bl_thread(void* arg) {
   if (w->phase == 1) outbuf = (uint8_t*)malloc(j->block_bytes + 64);
   for (uint64_t i = (uint64_t)w->tid; i < j->n_blocks; i += (uint64_t)j->threads) {
     const uint8_t* s = j->src + i * j->block_bytes;
+    const uint32_t codec = w->cj ? w->cj->codec : 1u;
     if (w->phase == 0) {
-      uint64_t cap = orc_lz4block_bound(j->block_bytes, j->lz4_block_size);
+      uint64_t cap = codec == 3   ? j->block_bytes + j->block_bytes / 128 + 1024
+                     : codec == 2 ? orc_xerial_bound(j->block_bytes, j->lz4_block_size)
+                                  : orc_lz4block_bound(j->block_bytes, j->lz4_block_size);
       if (!w->comp[i]) w->comp[i] = (uint8_t*)malloc(cap);
-      int64_t c = lz4block_compress_impl(s, j->block_bytes, j->lz4_block_size, w->comp[i], cap, 0, j->lz4_compress);
+      int64_t c;
+      if (codec == 3) {
+        size_t r = w->cj->zstd_compress(w->comp[i], cap, s, j->block_bytes, w->cj->level);
+        c = w->cj->zstd_is_error(r) ? -1 : (int64_t)r;
+      } else if (codec == 2) {
+        c = orc_xerial_compress2(s, j->block_bytes, j->lz4_block_size, w->comp[i], cap, 0);
+      } else {
+        c = lz4block_compress_impl(s, j->block_bytes, j->lz4_block_size, w->comp[i], cap, 0, j->lz4_compress);
+      }
       if (c < 0) {
         w->errors++;
         continue;
@@ -826,7 +838,15 @@ static void* bl_thread(void* arg) {
       if (j->checksum_alg) w->sums[i] = orc_checksum(j->checksum_alg, w->comp[i], (size_t)c);
     } else {
       if (j->checksum_alg && orc_checksum(j->checksum_alg, w->comp[i], (size_t)w->comp_len[i]) != w->sums[i]) w->errors++;
-      int64_t u = lz4block_walk(w->comp[i], w->comp_len[i], outbuf, j->block_bytes, j->lz4_decompress);
+      int64_t u;
+      if (codec == 3) {
+        size_t r = w->cj->zstd_decompress(outbuf, j->block_bytes, w->comp[i], w->comp_len[i]);
+        u = w->cj->zstd_is_error(r) ? -1 : (int64_t)r;
+      } else if (codec == 2) {
+        u = orc_xerial_decompress(w->comp[i], w->comp_len[i], outbuf, j->block_bytes);
+      } else {
+        u = lz4block_walk(w->comp[i], w->comp_len[i], outbuf, j->block_bytes, j->lz4_decompress);
+      }
       if (u != (int64_t)j->block_bytes || memcmp(outbuf, s, (size_t)j->block_bytes)) w->errors++;
     }
   }
@@ -834,7 +854,14 @@ static void* bl_thread(void* arg) {
   return NULL;
 }
 
-int orc_baseline_run(orc_baseline_job* job) {
+static int baseline_run_impl(orc_baseline_job* job, const orc_codec_job* cj);
+int orc_baseline_run(orc_baseline_job* job) { return baseline_run_impl(job, NULL); }
+int orc_baseline_run_codec(orc_codec_job* job) {
+  if (job->codec < 1 || job->codec > 3) return -2;
+  if (job->codec == 3 && (!job->zstd_compress || !job->zstd_decompress || !job->zstd_is_error)) return -2;
+  return baseline_run_impl(&job->base, job->codec == 1 ? NULL : job);
+}
+static int baseline_run_impl(orc_baseline_job* job, const orc_codec_job* cj) {
   int T = job->threads < 1 ? 1 : job->threads;
   job->threads = T;
   uint8_t** comp = (uint8_t**)calloc(job->n_blocks, sizeof(uint8_t*));
@@ -846,7 +873,7 @@ int orc_baseline_run(orc_baseline_job* job) {
   for (int phase = 0; phase < 2; phase++) {
     double t0 = now_s();
     for (int t = 0; t < T; t++) {
-      ws[t] = (bl_worker){job, t, comp, comp_len, sums, phase, 0};
+      ws[t] = (bl_worker){job, t, comp, comp_len, sums, phase, 0, cj};
       pthread_create(&th[t], NULL, bl_thread, &ws[t]);
     }
     for (int t = 0; t < T; t++) {

@@ -88,6 +88,8 @@ def lib():
         L.orc_gen_terasort.argtypes = [u8p, C.c_uint64, C.c_uint64, C.c_uint64]
         L.orc_baseline_run.restype = C.c_int
         L.orc_baseline_run.argtypes = [C.c_void_p]
+        L.orc_baseline_run_codec.restype = C.c_int
+        L.orc_baseline_run_codec.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -287,6 +289,32 @@ def _liblz4():
         return (C.cast(L.LZ4_compress_default, C.c_void_p).value, C.cast(L.LZ4_decompress_fast, C.c_void_p).value)
     except OSError:
         return (None, None)
+
+
+class _CodecJob(C.Structure):
+    _fields_ = [("base", _Job), ("codec", C.c_uint32), ("level", C.c_int32), ("zstd_compress", C.c_void_p),
+                ("zstd_decompress", C.c_void_p), ("zstd_is_error", C.c_void_p)]
+
+
+def _libzstd():
+    L = C.CDLL("libzstd.so.1")
+    return tuple(C.cast(getattr(L, n), C.c_void_p).value for n in ("ZSTD_compress", "ZSTD_decompress", "ZSTD_isError"))
+
+
+def baseline_run_codec(codec, data, block_bytes, block_size=32768, checksum_alg=CRC32C, threads=1, level=3):
+    """baseline_run for codec "lz4" | "snappy" | "zstd" (zstd = libzstd.so.1 at `level`, snappy = the restated
+    compressor under xerial framing).  Same result dict."""
+    if codec == "lz4":
+        return baseline_run(data, block_bytes, block_size, checksum_alg, threads, True)
+    a = _u8(data)
+    n_blocks = a.size // block_bytes
+    zc, zd, ze = _libzstd() if codec == "zstd" else (None, None, None)
+    job = _CodecJob(_Job(a.ctypes.data, block_bytes, n_blocks, block_size, checksum_alg, threads, None, None, 0, 0, 0, 0),
+                    {"snappy": 2, "zstd": 3}[codec], level, zc, zd, ze)
+    rc = lib().orc_baseline_run_codec(C.byref(job))
+    b = job.base
+    return dict(rc=rc, write_s=b.write_seconds, read_s=b.read_seconds, compressed_bytes=b.compressed_bytes,
+                errors=b.errors, liblz4=False, bytes=n_blocks * block_bytes)
 
 
 def baseline_run(data, block_bytes, lz4_block_size=32768, checksum_alg=CRC32C, threads=1, use_liblz4=True):

@@ -200,6 +200,15 @@ def test_cpu_baseline_driver_roundtrips(oracle):
         assert r["rc"] == 0 and r["errors"] == 0 and 0.3 < r["compressed_bytes"] / r["bytes"] < 0.7
 
 
+def test_cpu_baseline_driver_other_codecs(oracle):
+    """bench.py --codec snappy|zstd: the driver verifies every block it decodes (errors == 0 means bit-exact round
+    trips), zstd runs through libzstd.so.1"""
+    data = oracle.gen_terasort(7, 30 * 630)
+    for codec, lo, hi in (("lz4", 0.3, 0.7), ("snappy", 0.25, 0.7), ("zstd", 0.15, 0.5)):
+        r = oracle.baseline_run_codec(codec, data, 65520, threads=3)
+        assert r["rc"] == 0 and r["errors"] == 0 and lo < r["compressed_bytes"] / r["bytes"] < hi, (codec, r)
+
+
 def test_snappy_window_model_is_valid_snappy(oracle):
     """The CPU model of the GPU Snappy compressor (orc_snappy_compress_raw_win via xerial_compress(compressor=1))
     emits streams that the restated reader AND the real snappy library (pyarrow) decode."""
