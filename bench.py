@@ -347,6 +347,26 @@ def main():
                    "api": "b2s_compress_packed + b2s_decompress_packed on pinned host arenas (b2s_host_alloc)"}
             if n_e != n:
                 e2e["note"] = "pinned host memory did not allow the full %d blocks per rank; measured on %d" % (n, n_e)
+            if world == 1 and n_e >= 200:
+                # what ONE Spark task hands over: a map task's 200 partitions (commitAllPartitions), a reduce task's
+                # 80 map outputs (S3ShuffleReader.read) — latency of a single synchronous C-ABI call, median of 5
+                tws, trs = [], []
+                for _ in range(6):
+                    t = time.perf_counter()
+                    w1 = c.compress_packed(CODEC, h_src.array, off_e[:200], ln_e[:200], h_cmp.array, LZ4_BLOCK,
+                                           c.CHECKSUM_CRC32C)
+                    tws.append(time.perf_counter() - t)
+                    t = time.perf_counter()
+                    r1 = c.decompress_packed(CODEC, h_cmp.array, w1["dst_off"][:80], w1["dst_len"][:80], h_out.array,
+                                             c.CHECKSUM_CRC32C, sb_e[:81], w1["dst_len"][:80], w1["checksums"][:80])
+                    trs.append(time.perf_counter() - t)
+                    assert not w1["status"].any() and not r1["status"].any()
+                tw1, tr1 = statistics.median(tws[1:]), statistics.median(trs[1:])
+                e2e["task_sized_calls"] = {
+                    "map_task": {"blocks": 200, "uncompressed_MB": round(200 * block_bytes / 1e6, 1),
+                                 "ms": round(tw1 * 1e3, 2), "GBps": round(200 * block_bytes / tw1 / 1e9, 2)},
+                    "reduce_task": {"blocks": 80, "uncompressed_MB": round(80 * block_bytes / 1e6, 1),
+                                    "ms": round(tr1 * 1e3, 2), "GBps": round(80 * block_bytes / tr1 / 1e9, 2)}}
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1)
     cpu = None
