@@ -86,7 +86,7 @@ class B200CompressedOutputStream {
     emitted_++;
     in_.clear();
   }
-  const B200CompressionCodec& c_;
+  const B200CompressionCodec c_;  // by value: a stream may outlive the codec object that made it
   SinkFn sink_;
   PinnedArena in_, out_;
   bool closed_ = false;
@@ -139,7 +139,7 @@ class B200CompressedInputStream {
     if (status != 0) throw IOException("Stream is corrupted");
     total_ = dlen;
   }
-  const B200CompressionCodec& c_;
+  const B200CompressionCodec c_;
   SourceFn source_;
   PinnedArena in_, out_;
   bool decoded_ = false, closed_ = false;

@@ -227,7 +227,7 @@ class S3BufferedPrefetchIterator {
 
   S3BufferedPrefetchIterator(std::deque<Source> iter, int64_t maxBufferSize, int maxConcurrencyTask)
       : iter_(std::move(iter)), maxBufferSize_(maxBufferSize), startTime_(nanoTime()), hasItem_(!iter_.empty()),
-        threadPredictor_(maxConcurrencyTask) {
+        threadPredictor_(maxConcurrencyTask < 1 ? 1 : maxConcurrencyTask) {
     std::unique_lock<std::mutex> lk(mon_);
     configureThreads(-1, lk);  // :102-103 make sure that there's at least a single thread running
   }
