@@ -49,6 +49,24 @@ void b2sh_dispatcher_destroy(b2sh_dispatcher* d);
 int b2sh_dispatcher_get_path(b2sh_dispatcher* d, int kind, int32_t shuffle_id, int64_t map_id, char* buf, uint32_t cap);
 int b2sh_dispatcher_remove_shuffle(b2sh_dispatcher* d, int32_t shuffle_id);
 
+/* ---- group commit of the codec calls of concurrent task threads (threading row).  The dispatcher — one
+ * per executor, like the reference's singleton (helper/S3ShuffleDispatcher.scala:240-254) — owns a queue: the first
+ * caller runs at once, whatever other threads submit while the GPU is busy is merged into ONE b2s_compress_batch /
+ * b2s_decompress_batch in the next round (no timer, no added latency for a single thread).  Same arguments and per-stream
+ * results as the C-ABI batch calls; a call-level failure returns B2SH_E_CODEC.  The writer and the reader go through it
+ * when spark.shuffle.s3.gpu.coalesce=true (additive key, default false).  out4: calls, batches, largest number of
+ * calls merged into one batch, streams. ---- */
+int b2sh_dispatcher_queue_compress(b2sh_dispatcher* d, uint32_t codec, int32_t level, uint32_t codec_block_size,
+                                   uint32_t checksum_alg, uint32_t n, const uint8_t* const* src, const uint64_t* src_len,
+                                   uint8_t* const* dst, const uint64_t* dst_cap, uint64_t* dst_len,
+                                   uint64_t* checksum_out, int32_t* status);
+int b2sh_dispatcher_queue_decompress(b2sh_dispatcher* d, uint32_t codec, uint32_t checksum_alg, uint32_t n,
+                                     const uint8_t* const* src, const uint64_t* src_len, const uint32_t* n_slices,
+                                     const uint64_t* const* slice_len, const uint64_t* const* slice_checksum,
+                                     uint8_t* const* dst, const uint64_t* dst_cap, uint64_t* dst_len, int32_t* status,
+                                     int32_t* bad_slice);
+int b2sh_dispatcher_queue_statistics(b2sh_dispatcher* d, uint64_t* out4);
+
 /* ---- helper ---- */
 int b2sh_helper_checksum_algorithm(const char* name); /* -> B2S_CHECKSUM_* id or B2SH_E_UNSUPPORTED */
 int b2sh_helper_get_partition_lengths(b2sh_dispatcher* d, int32_t shuffle_id, int64_t map_id, int64_t* out,

@@ -41,6 +41,11 @@ PROTOTYPES = [
     ("b2sh_dispatcher_destroy", None, [_vp]),
     ("b2sh_dispatcher_get_path", C.c_int, [_vp, C.c_int, _i32, _i64, C.c_char_p, _u32]),
     ("b2sh_dispatcher_remove_shuffle", C.c_int, [_vp, _i32]),
+    ("b2sh_dispatcher_queue_compress", C.c_int,
+     [_vp, _u32, _i32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("b2sh_dispatcher_queue_decompress", C.c_int,
+     [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("b2sh_dispatcher_queue_statistics", C.c_int, [_vp, C.POINTER(_u64)]),
     ("b2sh_helper_checksum_algorithm", C.c_int, [C.c_char_p]),
     ("b2sh_helper_get_partition_lengths", C.c_int, [_vp, _i32, _i64, _vp, _u32, C.POINTER(_u32)]),
     ("b2sh_helper_get_checksums", C.c_int, [_vp, _i32, _i64, _vp, _u32, C.POINTER(_u32)]),
@@ -124,6 +129,41 @@ class S3ShuffleDispatcher:
 
     def removeShuffle(self, shuffleId):
         _check(load().b2sh_dispatcher_remove_shuffle(self._h, shuffleId))
+
+    # ---- the executor's group-commit queue (spark-s3-shuffle_b200/host/coalesce.h) ----
+    def queueStatistics(self):
+        v = (_u64 * 4)()
+        _check(load().b2sh_dispatcher_queue_statistics(self._h, v))
+        return dict(zip(("calls", "batches", "maxMerged", "streams"), list(v)))
+
+    def queueCompress(self, codec, parts, blockSize=32768, checksumAlg=0, bound=None):
+        """parts: list of bytes -> (streams, checksums, status); merged with whatever other threads submit meanwhile"""
+        n = len(parts)
+        srcs = [np.frombuffer(p, dtype=np.uint8) if len(p) else np.zeros(1, np.uint8) for p in parts]
+        lens = np.array([len(p) for p in parts], dtype=np.uint64)
+        caps = np.array([bound(len(p)) for p in parts], dtype=np.uint64)
+        dsts = [np.empty(max(int(c), 1), dtype=np.uint8) for c in caps]
+        sp = (_vp * n)(*[a.ctypes.data for a in srcs])
+        dp = (_vp * n)(*[a.ctypes.data for a in dsts])
+        dlen, cks, st = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.int32)
+        _check(load().b2sh_dispatcher_queue_compress(self._h, codec, 0, blockSize, checksumAlg, n, sp, lens.ctypes.data,
+                                                     dp, caps.ctypes.data, dlen.ctypes.data, cks.ctypes.data,
+                                                     st.ctypes.data))
+        return [d[: int(l)].tobytes() for d, l in zip(dsts, dlen)], [int(x) for x in cks], [int(x) for x in st]
+
+    def queueDecompress(self, codec, streams, sizes):
+        """streams: list of bytes, sizes: their decoded sizes -> (outputs, status)"""
+        n = len(streams)
+        srcs = [np.frombuffer(p, dtype=np.uint8) for p in streams]
+        lens = np.array([len(p) for p in streams], dtype=np.uint64)
+        caps = np.array(sizes, dtype=np.uint64)
+        dsts = [np.empty(max(int(c), 1), dtype=np.uint8) for c in caps]
+        sp = (_vp * n)(*[a.ctypes.data for a in srcs])
+        dp = (_vp * n)(*[a.ctypes.data for a in dsts])
+        dlen, st = np.zeros(n, np.uint64), np.zeros(n, np.int32)
+        _check(load().b2sh_dispatcher_queue_decompress(self._h, codec, 0, n, sp, lens.ctypes.data, None, None, None, dp,
+                                                       caps.ctypes.data, dlen.ctypes.data, st.ctypes.data, None))
+        return [d[: int(l)].tobytes() for d, l in zip(dsts, dlen)], [int(x) for x in st]
 
     def close(self):
         if self._h:

@@ -113,6 +113,7 @@ static void mkdirs(const std::string& dir) {
 }  // namespace b2s
 #include "streams.h"
 #include "codec_adapter.h"
+#include "coalesce.h"
 namespace b2s {
 namespace host {
 
@@ -148,6 +149,7 @@ class S3ShuffleDispatcher {
     gpuEnabled = getBool("spark.shuffle.s3.gpu.enabled", true);  // additive key
     gpuCodecBufferSize = (uint64_t)getSize("spark.shuffle.s3.gpu.codecBufferSize", 64L * 1024 * 1024);  // additive
     gpuReadBatchBlocks = getInt("spark.shuffle.s3.gpu.readBatchBlocks", 0);  // additive; 0 = all completed blocks
+    gpuCoalesce = getBool("spark.shuffle.s3.gpu.coalesce", false);  // additive: group-commit the calls of concurrent task threads
     if (!rootIsLocal && rootDir.find("://") != std::string::npos)
       throw UnsupportedOperationException("only file:// roots are implemented by the host mirror: " + rootDir);
   }
@@ -189,6 +191,8 @@ class S3ShuffleDispatcher {
   uint32_t lz4BlockSize = 32768;
   uint64_t gpuCodecBufferSize = 64ull << 20;
   int gpuReadBatchBlocks = 0;
+  bool gpuCoalesce = false;
+  CoalescingQueue queue;  // one per dispatcher = one per executor JVM (helper/S3ShuffleDispatcher.scala:240-254)
 
   // caches of S3ShuffleHelper (helper/S3ShuffleHelper.scala:15-16) live with the dispatcher instance here
   std::mutex cacheMutex;
@@ -303,6 +307,11 @@ static void ensure_codec_runtime() {
   if (rc != 0) throw CodecException(std::string("b2s_init: ") + b2s_strerror(rc) + ": " + b2s_last_error());
 }
 
+static void submit_or_throw(CoalescingQueue& q, CodecRequest& r, const char* what) {
+  const int rc = q.submit(r);
+  if (rc != 0) throw CodecException(std::string(what) + ": " + b2s_strerror(rc) + ": " + r.error);
+}
+
 // ---- S3ShuffleMapOutputWriter (shuffle/S3ShuffleMapOutputWriter.scala) --------------------------------------
 class S3ShuffleMapOutputWriter {
  public:
@@ -342,6 +351,7 @@ class S3ShuffleMapOutputWriter {
     std::vector<int64_t> checksums((size_t)numPartitions_, 0);
     const uint8_t* data = buf_.data();
     uint64_t data_len = buf_.size();
+    std::vector<std::pair<const uint8_t*, uint64_t>> segments{{data, data_len}};  // what goes into .data, in order
     if ((int64_t)data_len != totalBytesWritten_)
       throw RuntimeException("S3ShuffleMapOutputWriter: Unexpected output length " + std::to_string(data_len) +
                              ", expected: " + std::to_string(totalBytesWritten_) + ".");
@@ -364,9 +374,39 @@ class S3ShuffleMapOutputWriter {
       doff.resize(n); dlen.resize(n); cks.resize(n); status.resize(n);
       out_.resize(bound);
       uint64_t total = 0;
-      int rc = b2s_compress_packed((uint32_t)d_.codecId(), 0, d_.lz4BlockSize, alg, n, data, off.data(), len.data(),
-                                   out_.data(), bound, doff.data(), dlen.data(), &total, cks.data(), status.data());
-      if (rc != 0) throw CodecException(std::string("b2s_compress_packed: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+      if (d_.gpuCoalesce) {
+        // through the executor's group-commit queue: per-stream pointers, every output at its bound-sized slot
+        std::vector<const uint8_t*> sp(n);
+        std::vector<uint8_t*> dp(n);
+        std::vector<uint64_t> cap(n);
+        uint64_t o = 0;
+        for (uint32_t k = 0; k < n; k++) {
+          sp[k] = data + off[k];
+          cap[k] = b2s_compress_bound((uint32_t)d_.codecId(), d_.lz4BlockSize, len[k]);
+          dp[k] = out_.data() + o;
+          doff[k] = o;
+          o += cap[k];
+        }
+        CodecRequest r;
+        r.op = 0;
+        r.codec = (uint32_t)d_.codecId();
+        r.block_size = d_.lz4BlockSize;
+        r.checksum_alg = alg;
+        r.n = n;
+        r.src = sp.data();
+        r.src_len = len.data();
+        r.dst = dp.data();
+        r.dst_cap = cap.data();
+        r.dst_len = dlen.data();
+        r.checksum_out = cks.data();
+        r.status = status.data();
+        submit_or_throw(d_.queue, r, "b2s_compress_batch");
+        for (uint32_t k = 0; k < n; k++) total += dlen[k];
+      } else {
+        int rc = b2s_compress_packed((uint32_t)d_.codecId(), 0, d_.lz4BlockSize, alg, n, data, off.data(), len.data(),
+                                     out_.data(), bound, doff.data(), dlen.data(), &total, cks.data(), status.data());
+        if (rc != 0) throw CodecException(std::string("b2s_compress_packed: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+      }
       for (uint32_t k = 0; k < n; k++)
         if (status[k] != 0) throw IOException(std::string("compress failed: ") + b2s_strerror(status[k]));
       std::fill(partitionLengths_.begin(), partitionLengths_.end(), 0);
@@ -375,8 +415,9 @@ class S3ShuffleMapOutputWriter {
         partitionLengths_[(size_t)idx[k]] = (int64_t)dlen[k];
         checksums[(size_t)idx[k]] = (int64_t)cks[k];
       }
-      data = out_.data();
       data_len = total;
+      segments.clear();  // partition k's stream sits at out_ + doff[k] (back to back in the packed form)
+      for (uint32_t k = 0; k < n; k++) segments.push_back({out_.data() + doff[k], dlen[k]});
     } else if (checksums_in) {
       for (int32_t p = 0; p < numPartitions_; p++) checksums[(size_t)p] = checksums_in[p];
     }
@@ -391,7 +432,7 @@ class S3ShuffleMapOutputWriter {
       // initStream (:43-49): BufferedOutputStream(S3MeasureOutputStream(createBlock(shuffleBlock), name), bufferSize)
       measure_.reset(new S3MeasureOutputStream(path, BlockId{BlockId::Data, shuffleId_, mapId_, 0, 0}.name(),
                                                (size_t)d_.bufferSize));
-      measure_->write(data, data_len);
+      for (auto& sg : segments) measure_->write(sg.first, sg.second);
       measure_->flush();  // :102-107
       measure_->close();
     }
@@ -626,11 +667,33 @@ class S3ShuffleReader {
       dcap[k] = dlen[k];
       o += dlen[k];
     }
-    rc = b2s_decompress_batch((uint32_t)codec, alg, n, src.data(), len.data(), verify ? nsl.data() : nullptr,
-                              verify ? slen.data() : nullptr, verify ? ssum.data() : nullptr, dst.data(), dcap.data(),
-                              dlen.data(), status.data(), bad.data());
+    std::string rcText;
+    if (d_.gpuCoalesce) {
+      CodecRequest r;
+      r.op = 1;
+      r.codec = (uint32_t)codec;
+      r.checksum_alg = alg;
+      r.n = n;
+      r.src = src.data();
+      r.src_len = len.data();
+      r.dst = dst.data();
+      r.dst_cap = dcap.data();
+      r.dst_len = dlen.data();
+      r.n_slices = verify ? nsl.data() : nullptr;
+      r.slice_len = verify ? slen.data() : nullptr;
+      r.slice_checksum = verify ? ssum.data() : nullptr;
+      r.bad_slice = bad.data();
+      r.status = status.data();
+      rc = d_.queue.submit(r);
+      rcText = r.error;
+    } else {
+      rc = b2s_decompress_batch((uint32_t)codec, alg, n, src.data(), len.data(), verify ? nsl.data() : nullptr,
+                                verify ? slen.data() : nullptr, verify ? ssum.data() : nullptr, dst.data(), dcap.data(),
+                                dlen.data(), status.data(), bad.data());
+      if (rc != 0) rcText = b2s_last_error();
+    }
     for (auto& f : got) f.stream->close();  // onClose(bufferSize): the budget goes back to the prefetcher
-    if (rc != 0) throw CodecException(std::string("b2s_decompress_batch: ") + b2s_strerror(rc) + ": " + b2s_last_error());
+    if (rc != 0) throw CodecException(std::string("b2s_decompress_batch: ") + b2s_strerror(rc) + ": " + rcText);
     for (uint32_t k = 0; k < n; k++) {
       const BlockId& id = info_[got[k].tag].id;
       if (status[k] == B2S_E_CHECKSUM)  // storage/S3ChecksumValidationStream.scala:72-74
@@ -894,6 +957,64 @@ int b2sh_prefetch_statistics(b2sh_prefetch* p, uint64_t* out8, char* line, uint3
   return guarded([&] { fill_prefetch_stats(p->p->iter->statistics(), out8, line, cap); });
 }
 void b2sh_prefetch_destroy(b2sh_prefetch* p) { delete p; }
+
+int b2sh_dispatcher_queue_statistics(b2sh_dispatcher* d, uint64_t* out4) {
+  return guarded([&] {
+    const CoalescingQueue::Statistics st = d->d->queue.statistics();
+    out4[0] = st.calls;
+    out4[1] = st.batches;
+    out4[2] = st.maxMerged;
+    out4[3] = st.streams;
+  });
+}
+int b2sh_dispatcher_queue_compress(b2sh_dispatcher* d, uint32_t codec, int32_t level, uint32_t codec_block_size,
+                                   uint32_t checksum_alg, uint32_t n, const uint8_t* const* src, const uint64_t* src_len,
+                                   uint8_t* const* dst, const uint64_t* dst_cap, uint64_t* dst_len,
+                                   uint64_t* checksum_out, int32_t* status) {
+  return guarded([&] {
+    ensure_codec_runtime();
+    CodecRequest r;
+    r.op = 0;
+    r.codec = codec;
+    r.level = level;
+    r.block_size = codec_block_size;
+    r.checksum_alg = checksum_alg;
+    r.n = n;
+    r.src = src;
+    r.src_len = src_len;
+    r.dst = dst;
+    r.dst_cap = dst_cap;
+    r.dst_len = dst_len;
+    r.checksum_out = checksum_out;
+    r.status = status;
+    submit_or_throw(d->d->queue, r, "b2s_compress_batch");
+  });
+}
+int b2sh_dispatcher_queue_decompress(b2sh_dispatcher* d, uint32_t codec, uint32_t checksum_alg, uint32_t n,
+                                     const uint8_t* const* src, const uint64_t* src_len, const uint32_t* n_slices,
+                                     const uint64_t* const* slice_len, const uint64_t* const* slice_checksum,
+                                     uint8_t* const* dst, const uint64_t* dst_cap, uint64_t* dst_len, int32_t* status,
+                                     int32_t* bad_slice) {
+  return guarded([&] {
+    ensure_codec_runtime();
+    CodecRequest r;
+    r.op = 1;
+    r.codec = codec;
+    r.checksum_alg = checksum_alg;
+    r.n = n;
+    r.src = src;
+    r.src_len = src_len;
+    r.dst = dst;
+    r.dst_cap = dst_cap;
+    r.dst_len = dst_len;
+    r.n_slices = n_slices;
+    r.slice_len = slice_len;
+    r.slice_checksum = slice_checksum;
+    r.bad_slice = bad_slice;
+    r.status = status;
+    submit_or_throw(d->d->queue, r, "b2s_decompress_batch");
+  });
+}
 
 int b2sh_codec_create(b2sh_dispatcher* d, b2sh_codec** out) {
   return guarded([&] {

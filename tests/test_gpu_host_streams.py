@@ -225,3 +225,98 @@ def test_c_abi_is_reentrant_across_task_threads(capi, oracle):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+# ---- group commit across task threads ------------------------------------------------------------------------------
+def test_group_commit_merges_the_calls_of_concurrent_task_threads(tmp_path, capi, oracle):
+    """spark-s3-shuffle_b200/host/coalesce.h: calls submitted while the GPU is busy are merged into one C-ABI batch;
+    every caller still gets exactly its own streams, checksums and status."""
+    d = host.S3ShuffleDispatcher(conf_for(tmp_path))
+    errors, n_threads, reps = [], 8, 6
+
+    def task(t):
+        try:
+            for rep in range(reps):
+                parts = [corpus(oracle, ("terasort", "text", "ints")[(t + i) % 3], 150_000 + 7_000 * i + 13 * t, seed=t * 17 + i)
+                         for i in range(5)]
+                comp, cks, st = d.queueCompress(capi.CODEC_LZ4BLOCK, parts, 32768, capi.CHECKSUM_CRC32,
+                                                bound=lambda n: int(capi.compress_bound(capi.CODEC_LZ4BLOCK, 32768, n)))
+                assert st == [0] * 5
+                assert [oracle.lz4block_decompress(s) for s in comp] == parts      # the unmodified reader's arithmetic
+                assert cks == [oracle.crc32(s) for s in comp]
+                out, st = d.queueDecompress(capi.CODEC_LZ4BLOCK, comp, [len(p) for p in parts])
+                assert st == [0] * 5 and out == parts
+        except BaseException as e:  # noqa: BLE001 - reported on the main thread
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=task, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    st = d.queueStatistics()
+    assert st["calls"] == n_threads * reps * 2 and st["streams"] == st["calls"] * 5
+    assert st["batches"] < st["calls"] and st["maxMerged"] >= 2, st     # something was merged
+    d.close()
+
+
+def test_writer_and_reader_through_the_group_commit_queue(tmp_path):
+    """spark.shuffle.s3.gpu.coalesce=true: four map tasks commit and four reduce tasks read concurrently through one
+    dispatcher; files and results are the same as without the queue."""
+    d = host.S3ShuffleDispatcher(conf_for(tmp_path, **{"spark.shuffle.s3.gpu.coalesce": True}))
+    n_maps, n_red, per = 8, 4, 30_000
+    errors = []
+
+    def map_task(m):
+        try:
+            i = np.arange(m * per, (m + 1) * per, dtype=np.int64)
+            w = host.S3ShuffleMapOutputWriter(d, 0, m, n_red)
+            for r in range(n_red):
+                sel = i[i % n_red == r]
+                with w.getPartitionWriter(r) as s:
+                    s.write(encode_pairs(sel % 977, sel))
+            w.commitAllPartitions()
+            w.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(("map", m, repr(e)))
+
+    ths = [threading.Thread(target=map_task, args=(m,)) for m in range(n_maps)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errors, errors
+    got = {}
+
+    def reduce_task(r):
+        try:
+            rd = host.S3ShuffleReader(d, 0, list(range(n_maps)), r, r + 1)
+            got[r] = np.sort(np.concatenate([decode_pairs(b)[1] for _, b in rd.read()]))
+            rd.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(("reduce", r, repr(e)))
+
+    ths = [threading.Thread(target=reduce_task, args=(r,)) for r in range(n_red)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errors, errors
+    allv = np.arange(n_maps * per, dtype=np.int64)
+    for r in range(n_red):
+        assert np.array_equal(got[r], allv[allv % n_red == r])
+    st = d.queueStatistics()
+    assert st["calls"] >= n_maps + n_red
+    # the same files without the queue: byte-identical .data objects
+    d2 = host.S3ShuffleDispatcher(conf_for(tmp_path, **{"spark.app.id": "app-direct"}))
+    i = np.arange(0, per, dtype=np.int64)
+    w = host.S3ShuffleMapOutputWriter(d2, 0, 0, n_red)
+    for r in range(n_red):
+        with w.getPartitionWriter(r) as s:
+            s.write(encode_pairs(i[i % n_red == r] % 977, i[i % n_red == r]))
+    w.commitAllPartitions()
+    w.close()
+    assert open(d2.getPath("data", 0, 0), "rb").read() == open(d.getPath("data", 0, 0), "rb").read()
+    d.close()
+    d2.close()

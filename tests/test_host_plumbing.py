@@ -173,6 +173,18 @@ def test_gpu_mode_fails_loudly_without_a_device(tmp_path):
     d.close()
 
 
+def test_group_commit_queue_fails_loudly_without_a_device(tmp_path):
+    """the queue is plumbing over the C ABI: no GPU, no result (never a CPU path)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    d = host.S3ShuffleDispatcher(new_conf(tmp_path))
+    with pytest.raises(host.CodecException):
+        d.queueCompress(1, [b"abc" * 100], bound=lambda n: n + 64)
+    assert d.queueStatistics()["batches"] == 0
+    d.close()
+
+
 def test_single_spill_transfer_moves_file_and_writes_metadata(tmp_path, oracle):
     """shuffle/S3SingleSpillShuffleMapOutputWriter.scala:24-64 — the spill file (already compressed + checksummed by
     Spark's UnsafeShuffleWriter, played by the oracle) becomes the .data object; .checksum and .index follow."""
