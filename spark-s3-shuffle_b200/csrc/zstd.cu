@@ -94,13 +94,14 @@ __global__ void __launch_bounds__(kZWarps * 32) zstd_entropy_kernel(const uint8_
 __global__ void __launch_bounds__(128) zstd_sum_kernel(const zstd::BlockInfo* __restrict__ blocks,
                                                        const uint64_t* __restrict__ cnt,
                                                        const uint64_t* __restrict__ base, uint32_t n,
-                                                       uint64_t* __restrict__ olen, const int32_t* __restrict__ status) {
+                                                       uint64_t* __restrict__ olen, int32_t* __restrict__ status) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t sum = 0;
   if (status[i] == 0) {
-    const zstd::BlockInfo* b = blocks + base[i];
-    for (uint64_t k = 0; k < cnt[i]; k++) sum += b[k].out_size;
+    const int64_t r = zstd::stream_size(blocks + base[i], cnt[i]);
+    if (r < 0) status[i] = zstd_status(r);  // a frame's blocks do not add up to its Frame_Content_Size
+    else sum = (uint64_t)r;
   }
   olen[i] = sum;
 }
@@ -176,7 +177,7 @@ void launch_zstd_entropy(bool size_only, const uint8_t* src_base, void* d_blocks
   *launches += 1;
 }
 void launch_zstd_sum(const void* d_blocks, const uint64_t* d_cnt, const uint64_t* d_base, uint32_t n, uint64_t* d_olen,
-                     const int32_t* d_status, cudaStream_t st, uint64_t* launches) {
+                     int32_t* d_status, cudaStream_t st, uint64_t* launches) {
   if (!n) return;
   zstd_sum_kernel<<<(n + 127) / 128, 128, 0, st>>>((const zstd::BlockInfo*)d_blocks, d_cnt, d_base, n, d_olen, d_status);
   *launches += 1;

@@ -395,6 +395,20 @@ B2S_HD inline int64_t entropy_block(Workspace* w, const BlockInfo* blocks, uint3
   return (int64_t)total;
 }
 
+// Decoded size of a stream from its blocks' sizes (after the entropy stage); checks every declared Frame_Content_Size.
+B2S_HD inline int64_t stream_size(const BlockInfo* blocks, uint64_t nb) {
+  uint64_t sum = 0, frame = 0;
+  for (uint64_t k = 0; k < nb; k++) {
+    frame += blocks[k].out_size;
+    if (blocks[k].last) {
+      if (blocks[k].has_fcs && frame != blocks[k].fcs) return kErrCorrupt;
+      sum += frame;
+      frame = 0;
+    }
+  }
+  return (int64_t)(sum + frame);
+}
+
 // one step of the repeat-offset state machine (RFC 8878 3.1.1.5); returns the resolved offset (0 = corrupt)
 B2S_HD inline uint32_t resolve_offset(uint32_t ofv, bool ll0, uint32_t* r0, uint32_t* r1, uint32_t* r2) {
   uint32_t offset;

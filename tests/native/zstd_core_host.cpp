@@ -55,7 +55,7 @@ extern "C" long long zc_decode_par(const unsigned char* src, unsigned long long 
     total += r;
   }
   free(w);
-  if (size_only) return total;
+  if (size_only) return stream_size(blocks.data(), t.nblk);
   return execute_stream(blocks.data(), (uint32_t)t.nblk, src, lit.data(), ll.data(), ml.data(), ofv.data(), dst, cap);
 }
 
