@@ -17,6 +17,8 @@
  *   S3BufferedPrefetchIterator storage/S3BufferedPrefetchIterator.scala:16-213 (threads, memory budget, LIFO, ThreadPredictor)
  *   S3BufferedInputStreamAdaptor  storage/S3BufferedInputStreamAdaptor.scala:7-59 (owns the block buffer, returns budget on close)
  *   B200CompressionCodec       the Spark CompressionCodec seam [U] of SURVEY.md §8(f)-1 (compressedOutputStream / compressedInputStream)
+ *   CoalescingQueue            (no counterpart in the reference) group commit of the codec calls of concurrent task threads,
+ *                              owned by the dispatcher like the reference's executor-wide singletons; SURVEY.md §8(b) threading
  * Only file:// roots are implemented (S3/Hadoop I/O is out of scope).
  *
  * Errors: functions return 0 or a negative B2SH_E_* code; b2sh_last_error() holds the reference's exception text
