@@ -42,3 +42,27 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     out = json.loads(lines[0])
     assert out["impl"] == "reference" and out["n_gpus"] == 2 and out["value"] > 0
     assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["cpu_baseline"]["kind"] == "port"
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("codec", ["lz4", "snappy", "zstd"])
+def test_reference_arm_contract_for_every_codec(codec):
+    """`bench.py --impl reference --codec X`: one JSON line with the driver's keys, timed on the CPU arithmetic of that
+    codec (liblz4 / restated snappy / libzstd)"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--codec", codec, "--steps", "1",
+                        "--warmup", "1", "--blocks", "30", "--cpu-sample-blocks", "30"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert k in out, k
+    assert out["impl"] == "reference" and out["value"] > 0 and out["unit"] == "GB/s" and out["dtype"] == "u8"
+    assert out["cpu_baseline"]["cores"] >= 1 and 0.1 < out["cpu_baseline"]["compressed_ratio"] < 0.9
+    assert {"lz4": "liblz4", "snappy": "Snappy", "zstd": "libzstd"}[codec] in out["cpu_baseline"]["note"]
