@@ -52,6 +52,7 @@ struct FseEntry {
   uint8_t sym, nbits;
   uint16_t base;
 };
+static_assert(sizeof(FseEntry) == 4, "zstd_par.h reads an entry as one little-endian 32-bit word");
 
 // per-stream decoder state: ~11 KB of tables (shared memory on the device) + a pointer to the literals buffer
 struct Workspace {

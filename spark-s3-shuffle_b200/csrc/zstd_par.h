@@ -351,8 +351,14 @@ B2S_HD inline int64_t entropy_block(Workspace* w, const BlockInfo* blocks, uint3
     uint32_t sl = br.read(w->ll_log), so = br.read(w->of_log), sm = br.read(w->ml_log);
     uint32_t my_ll = 0, my_ml = 0, my_ofv = 0;
     int nb = 0;
+    // one 32-bit load per table entry (sym | nbits << 8 | base << 16): the entry feeds both the symbol and, at the end of
+    // the iteration, the state update — through a generic pointer the compiler would otherwise re-read it field by field
+    const uint32_t* tll = reinterpret_cast<const uint32_t*>(w->ll);
+    const uint32_t* tof = reinterpret_cast<const uint32_t*>(w->of);
+    const uint32_t* tml = reinterpret_cast<const uint32_t*>(w->ml);
     for (uint32_t i = 0; i < b.nseq; i++) {
-      const int oc = w->of[so].sym, mc = w->ml[sm].sym, lc = w->ll[sl].sym;
+      const uint32_t eo = tof[so], em = tml[sm], el = tll[sl];
+      const int oc = (int)(eo & 0xffu), mc = (int)(em & 0xffu), lc = (int)(el & 0xffu);
       if (oc > 31 || mc > 52 || lc > 35) return kErrCorrupt;
       uint32_t mlb, llb;
       int mle, lle;
@@ -382,10 +388,10 @@ B2S_HD inline int64_t entropy_block(Workspace* w, const BlockInfo* blocks, uint3
           nb = 0;
         }
       }
-      if (i + 1 < b.nseq) {
-        sl = w->ll[sl].base + br.read(w->ll[sl].nbits);
-        sm = w->ml[sm].base + br.read(w->ml[sm].nbits);
-        so = w->of[so].base + br.read(w->of[so].nbits);
+      if (i + 1 < b.nseq) {  // state updates: literal length, match length, offset
+        sl = (el >> 16) + br.read((int)((el >> 8) & 0xffu));
+        sm = (em >> 16) + br.read((int)((em >> 8) & 0xffu));
+        so = (eo >> 16) + br.read((int)((eo >> 8) & 0xffu));
       }
     }
     if (br.pos != 0) return kErrCorrupt;
