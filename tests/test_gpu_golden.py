@@ -52,3 +52,25 @@ def test_gpu_reencodes_golden_inputs(capi, oracle):
         assert s == oracle.crc32(c)
         assert c == oracle.lz4block_compress(x, 32768, compressor=1), k
     assert comp[NAMES.index("empty")].hex() == GOLDEN["kat"]["lz4block_empty_stream_hex"]
+
+
+def test_gpu_decodes_committed_libzstd_frames(capi):
+    """tests/golden/zstd_vectors.json — frames written by libzstd.so.1 (what zstd-jni wraps), committed with the script
+    that made them (tests/golden/make_golden_zstd.py): sized and decoded through the C ABI, CRC-32 of every output"""
+    import json
+    import os
+    import zlib
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "zstd_vectors.json")))
+    names, frames, want_len, want_crc = [], [], [], []
+    for name, c in sorted(gold["cases"].items()):
+        for kind, hexframe in sorted(c["frames"].items()):
+            names.append((name, kind))
+            frames.append(bytes.fromhex(hexframe))
+            want_len.append(c["input_len"])
+            want_crc.append(c["crc32"])
+    sizes, st = capi.decompressed_size_batch(capi.CODEC_ZSTD, frames)
+    assert st == [0] * len(frames) and sizes == want_len
+    out, st, _ = capi.decompress_batch(capi.CODEC_ZSTD, frames)
+    assert st == [0] * len(frames)
+    for nm, o, n, crc in zip(names, out, want_len, want_crc):
+        assert len(o) == n and zlib.crc32(o) == crc, nm

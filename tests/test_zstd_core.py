@@ -179,3 +179,20 @@ def test_block_parallel_decoder_with_shared_table_storage(tmp_path, oracle):
                 buf = C.create_string_buffer(max(n, 1))
                 assert L.zc_decode_par(f, len(f), buf, n, 0) == n and buf.raw[:n] == d
                 assert L.zc_decode_par(f, len(f), None, 0, 1) == n
+
+
+def test_committed_libzstd_frames(zc):
+    """tests/golden/zstd_vectors.json (made by tests/golden/make_golden_zstd.py from libzstd.so.1): both decoder
+    statements reproduce every input, sized and decoded"""
+    import json
+    import zlib
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "zstd_vectors.json")))
+    n = 0
+    for name, c in gold["cases"].items():
+        for kind, hexframe in c["frames"].items():
+            f = bytes.fromhex(hexframe)
+            r, out = decode(zc, f, c["input_len"])
+            assert r == c["input_len"] and zlib.crc32(out) == c["crc32"], (name, kind, r)
+            assert zc.zc_size(f, len(f)) == c["input_len"]
+            n += 1
+    assert n == 40
