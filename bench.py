@@ -1,15 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — shuffle write+read GB/s (compress + CRC / verify + decompress) on BASELINE.json config[1]:
-terasort-shaped data, 10 GiB, 80 maps x 200 partitions = 16,000 shuffle blocks, LZ4Block 32 KiB + CRC32C, 1 x B200
-(per GPU; with --gpus N every rank processes its own 10 GiB => weak scaling, no data-path collective).
+"""bench.py — shuffle write+read GB/s (compress + CRC / verify + decompress) on BASELINE.json's configurations.
 
-One "step" = one write pass (b2s_compress_*: XXH32 + LZ4 + framing + CRC32C over the compressed streams) plus one read
-pass (b2s_decompress_*: CRC32C verify + LZ4 decode + XXH32 verify) over the whole dataset.
+  --config 2 (default at --gpus 1): terasort 10 GiB per GPU, 80 maps x 200 partitions = 16,000 shuffle blocks of 671,112 B,
+                                    LZ4Block 32 KiB + CRC32C ("terasort 10 GB, 200 partitions, LZ4 + CRC32C, 1xB200"); with
+                                    --gpus N every rank owns its own 10 GiB (weak scaling)
+  --config 3 (default at --gpus >1): terasort 100 GiB, 800 maps x 2000 partitions = 1.6 M shuffle blocks of 65,520 B (two full
+                                    LZ4 blocks + end mark each), block i -> GPU i mod N (strong scaling: the total is fixed).  A
+                                    rank keeps one WAVE of <= 200,000 blocks (13 GB) resident and runs ceil(share / wave) passes
+                                    per step ("stream the dataset in waves and accumulate time")
+  --config 4: the SQL-join exchange volume of config 4 — 50 GiB, 80,000 shuffle blocks, Snappy (xerial), split i mod N
+  --config 5: Zstandard, shuffle-block size sweep 4 KiB .. 64 MiB on one GPU (value = the 640 KiB point)
+
+One "step" = one write pass (b2s_compress_*: XXH32 + match/parse/emit + framing + CRC32C over the compressed streams) plus
+one read pass (b2s_decompress_*: CRC32C verify + decode + XXH32 verify) over the rank's whole share.
   value : uncompressed bytes / (t_write + t_read), inputs and outputs resident in HBM (device API)
-  e2e   : the same through the host-pointer C ABI a JVM would call (pinned host buffers; H2D and D2H inside the timed region)
-  roofline : dominant kernel (lz4_compress_kernel) algorithmic bytes (1+r)*U per launch / CUDA-event duration vs measured HBM peak
-  cpu_baseline : the reference's CPU arithmetic (liblz4 LZ4_compress_default/LZ4_decompress_fast + LZ4Block framing +
-                 XXH32 + CRC32C, oracle/), all host cores, bounded sample of the same data
+  e2e   : the same through the host-pointer C ABI a JVM would call (NUMA-local pinned host arenas; H2D and D2H inside the
+          timed region).  e2e.value is the write||read figure — a map-side compress call and a reduce-side decompress call
+          in flight together from two task threads, the way an executor's task slots use the two lanes of the ABI and both
+          directions of the PCIe link; e2e.serial is one call at a time (round 1's figure)
+  roofline : dominant kernel algorithmic bytes (1+r)*U per launch / CUDA-event duration vs measured HBM peak
+  cpu_baseline : the reference's CPU arithmetic (liblz4 / libzstd / restated snappy + framing + XXH32 + CRC32C, oracle/), all
+                 host cores the cgroup grants, bounded sample of the same data
 `--impl reference` times that CPU path alone on the same config (the reference itself is Scala on a JVM, absent here).
 """
 import argparse
@@ -27,13 +38,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RECORD = 104
-RECORDS_PER_BLOCK = 6453            # 671,112 B per shuffle block
-N_BLOCKS_FULL = 16000               # 80 maps x 200 reduce partitions  => 10.0003 GiB
 LZ4_BLOCK = 32768
-# dram__bytes_read.sum + dram__bytes_write.sum of one lz4_match_kernel launch over a 1.25 GiB chunk (ncu --set full,
-# profiles/r1c_*), scaled to the bench's 1 GiB chunks at run time; None until a capture of the current kernel exists
-NCU_TRAFFIC_PER_LAUNCH = 6089710000  # 1.948 GB read + 4.141 GB written, full 32,768-block launch (profiles/r1p_multikernel_lz4.md)
+# ncu --set full of one lz4_match2_kernel launch over 32,768 codec blocks: dram__bytes_read 1.564 GB + dram__bytes_write
+# 2.060 GB (profiles/r2_match_parse.md); scaled to the blocks one launch of this run processes
+NCU_TRAFFIC_PER_CODEC_BLOCK = (1.564307e9 + 2.059700e9) / 32768
 METRIC = "shuffle write+read GB/s (compress+CRC) at 1/2/4/8 B200 vs JVM-LZ4 CPU baseline"
+WAVE_BLOCKS_SMALL = 200000   # 65,520-B blocks per resident wave (13.1 GB)
+WAVE_BLOCKS_LARGE = 20000    # 671,112-B blocks per resident wave (13.4 GB)
 
 
 def measured_peak():
@@ -44,6 +55,21 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def usable_cores():
+    """host threads this process may really use: the affinity mask, capped by the cgroup CPU quota (a 1-GPU lease of the
+    128-thread host gets cpu.max = 16 cores: round 1 printed 128 there and measured 14 cores' worth)"""
+    n = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    cores = n if quota is None else max(1, min(n, int(quota + 0.5)))
+    return cores, n, quota
 
 
 class ClockSampler:
@@ -91,7 +117,6 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-CPU_CODEC = "lz4"  # set from --codec
 CPU_NOTES = {
     "lz4": "oracle framing/XXH32/CRC32C + liblz4.so.1 LZ4_compress_default/LZ4_decompress_fast (the native routines "
            "lz4-java's JNI path calls); no JVM stream wrappers / JNI => upper bound on the reference",
@@ -102,11 +127,11 @@ CPU_NOTES = {
 }
 
 
-def cpu_arm(oracle, sample, block_bytes, threads, repeats=1):
+def cpu_arm(oracle, codec, sample, block_bytes, threads, repeats=1):
     """reference CPU arithmetic on `sample` (numpy uint8): returns (GB/s write+read, detail)"""
     best = None
     for _ in range(repeats):
-        r = oracle.baseline_run_codec(CPU_CODEC, sample, block_bytes, LZ4_BLOCK, oracle.CRC32C, threads=threads, level=3)
+        r = oracle.baseline_run_codec(codec, sample, block_bytes, LZ4_BLOCK, oracle.CRC32C, threads=threads, level=3)
         if r["rc"] != 0:
             raise RuntimeError("CPU baseline reported %d errors" % r["errors"])
         t = r["write_s"] + r["read_s"]
@@ -116,44 +141,82 @@ def cpu_arm(oracle, sample, block_bytes, threads, repeats=1):
     return r["bytes"] / t / 1e9, r
 
 
+def plan(args, world):
+    """-> dict(codec, records_per_block, blocks (per rank, per wave), waves, scaling, workload text)"""
+    cfg = args.config if args.config else (2 if world == 1 else 3)
+    if cfg == 2:
+        rpb, codec, total_blocks = 6453, "lz4", 16000 * world
+        per_rank, scaling = 16000, "weak"
+        what = "config 2: terasort 10.00 GiB per GPU, 80 maps x 200 partitions = 16,000 shuffle blocks x 671,112 B"
+    elif cfg == 3:
+        rpb, codec, total_blocks = 630, "lz4", 1600000
+        per_rank, scaling = -(-total_blocks // world), "strong"
+        what = ("config 3: terasort 100 GiB, 800 maps x 2000 partitions = 1,600,000 shuffle blocks x 65,520 B "
+                "(2 full LZ4 blocks + end mark each), block i -> GPU i mod %d" % world)
+    elif cfg == 4:
+        rpb, codec, total_blocks = 6453, "snappy", 80000
+        per_rank, scaling = -(-total_blocks // world), "strong"
+        what = ("config 4: SQL-join exchange volume 50 GiB, 400 maps x 200 partitions = 80,000 shuffle blocks x 671,112 B "
+                "(terasort-shaped records; the UnsafeRow shape is covered by tests/test_gpu_snappy.py), block i -> GPU i mod %d" % world)
+    else:
+        raise SystemExit("--config 5 is the block-size sweep: run tools/zstd_sweep.py (bench.py --config 5 forwards to it)")
+    if args.codec:
+        codec = args.codec
+    if args.records_per_block:
+        rpb = args.records_per_block
+    if args.blocks:
+        per_rank = args.blocks
+    cap = WAVE_BLOCKS_SMALL if rpb * RECORD < 200000 else WAVE_BLOCKS_LARGE
+    waves = max(1, -(-per_rank // cap))
+    wave_blocks = -(-per_rank // waves)
+    return {"config": cfg, "codec": codec, "rpb": rpb, "wave_blocks": wave_blocks, "waves": waves, "scaling": scaling,
+            "what": what, "per_rank": wave_blocks * waves}
+
+
 def main():
-    global RECORDS_PER_BLOCK, CPU_CODEC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--blocks", type=int, default=int(os.environ.get("B2S_BENCH_BLOCKS", N_BLOCKS_FULL)),
-                    help="shuffle blocks per GPU (16000 = the 10 GiB config; smaller only for quick checks)")
-    ap.add_argument("--records-per-block", type=int, default=RECORDS_PER_BLOCK,
-                    help="104-byte records per shuffle block: 6453 = config 2 (default), 630 = config 3's ~64 KiB blocks")
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-blocks", type=int, default=6000)
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
+                    help="BASELINE.json configuration; 0 = config 2 at --gpus 1, config 3 at --gpus > 1")
+    ap.add_argument("--blocks", type=int, default=int(os.environ.get("B2S_BENCH_BLOCKS", 0)),
+                    help="shuffle blocks per GPU (overrides the configuration; smaller only for quick checks)")
+    ap.add_argument("--records-per-block", type=int, default=0,
+                    help="104-byte records per shuffle block (overrides the configuration): 6453 = 671,112 B, 630 = 65,520 B")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample-bytes", type=int, default=4 << 30, help="uncompressed bytes of the CPU arm's sample per step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--codec", default="lz4", choices=["lz4", "snappy", "zstd"],
-                    help="lz4 = the BASELINE configuration; snappy / zstd report the other codecs on the same data")
+    ap.add_argument("--codec", default="", choices=["", "lz4", "snappy", "zstd"],
+                    help="override the configuration's codec (lz4 = LZ4Block, snappy = xerial, zstd)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config == 5:
+        if rank == 0:
+            os.execv(sys.executable, [sys.executable, os.path.join(ROOT, "tools", "zstd_sweep.py"), "--bench-line"])
+        return 0
     steps, warmup = args.steps, max(args.warmup, 3)
-    n = args.blocks
-    RECORDS_PER_BLOCK = args.records_per_block
-    CPU_CODEC = args.codec
-    block_bytes = RECORDS_PER_BLOCK * RECORD
-    total = n * block_bytes
-    workload = "terasort %.2f GiB/GPU, %d shuffle blocks x %d B (%s), LZ4Block 32 KiB + CRC32C" % (
-        total / 2**30, n, block_bytes,
-        "80 maps x 200 partitions" if RECORDS_PER_BLOCK == 6453 else "config-3 shape: 2 full LZ4 blocks + end mark per block")
+    P = plan(args, world)
+    codec_name, rpb, n, waves = P["codec"], P["rpb"], P["wave_blocks"], P["waves"]
+    block_bytes = rpb * RECORD
+    wave_bytes = n * block_bytes
+    rank_bytes = wave_bytes * waves
     codec_desc = {"lz4": "lz4 (LZ4Block, blockSize 32 KiB)", "snappy": "snappy (xerial framing, blockSize 32 KiB)",
-                  "zstd": "zstd (frames of 32 KiB blocks; raw literals + predefined-FSE sequences)"}[args.codec]
-    if args.codec != "lz4":
-        workload = workload.replace("LZ4Block 32 KiB", codec_desc)
-    config = {"workload": workload, "codec": codec_desc, "checksum": "CRC32C over compressed bytes",
-              "blocks_per_gpu": n, "block_bytes": block_bytes, "l2_policy": "inputs (>= 6 GiB per pass) far larger than the 126 MB L2",
+                  "zstd": "zstd (frames of 32 KiB blocks)"}[codec_name]
+    workload = "%s; %s + CRC32C" % (P["what"], codec_desc)
+    config = {"workload": workload, "baseline_config": P["config"], "codec": codec_desc,
+              "checksum": "CRC32C over compressed bytes", "blocks_per_gpu": n * waves, "block_bytes": block_bytes,
+              "waves_per_step": waves, "wave_blocks": n,
+              "l2_policy": "every pass streams >= 6 GB per GPU, far larger than the 126 MB L2",
               "sharding": "block i -> GPU i mod N (each rank owns its blocks; no collective on the data path)"}
+    if waves > 1:
+        config["waves_note"] = ("a rank's share (%.1f GB) is processed as %d passes over one resident wave of %d blocks"
+                                % (rank_bytes / 1e9, waves, n))
 
     from oracle import oracle  # CPU baseline legs only (never on the GPU product path)
 
@@ -161,24 +224,24 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        threads = os.cpu_count() or 1
-        sample_blocks = min(args.cpu_sample_blocks, n)
-        sample = oracle.gen_terasort(0, sample_blocks * RECORDS_PER_BLOCK)
-        for _ in range(max(1, min(warmup, 1))):
-            cpu_arm(oracle, sample[: 200 * block_bytes], block_bytes, threads)
+        threads, aff, quota = usable_cores()
+        sample_blocks = max(1, min(args.cpu_sample_bytes // block_bytes, n))
+        sample = oracle.gen_terasort(0, sample_blocks * rpb)
+        cpu_arm(oracle, codec_name, sample[: min(sample_blocks, 200) * block_bytes], block_bytes, threads)
         vals, t0 = [], time.perf_counter()
         for _ in range(steps):
-            v, detail = cpu_arm(oracle, sample, block_bytes, threads)
+            v, detail = cpu_arm(oracle, codec_name, sample, block_bytes, threads)
             vals.append(v)
         wall = time.perf_counter() - t0
         value = sample.size * steps / sum(sample.size / (v * 1e9) for v in vals) / 1e9
-        sample_desc = "%d of %d shuffle blocks (%.2f GiB) per step, same generator/seed" % (sample_blocks, n, sample.size / 2**30)
+        sample_desc = "%d of %d shuffle blocks (%.2f GiB) per step, same generator/seed" % (
+            sample_blocks, n * waves * world, sample.size / 2**30)
         line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": args.gpus,
                 "steps": steps, "warmup": warmup, "ms_per_step": round(wall / steps * 1e3, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "scaling": P["scaling"], "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": threads,
-                                 "kind": "port", "sample": sample_desc,
-                                 "note": CPU_NOTES[args.codec],
+                                 "affinity_threads": aff, "cgroup_cpu_quota": quota, "kind": "port", "sample": sample_desc,
+                                 "note": CPU_NOTES[codec_name],
                                  "compressed_ratio": round(detail["compressed_bytes"] / detail["bytes"], 4)},
                 "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -194,12 +257,15 @@ def main():
     c = pkg.capi
     c.init(1 << local_rank)
     L = c.load()
+    # the rank's host threads and pinned arenas live on the socket its GPU hangs off
+    numa_node = c.bind_thread_to_device(0)
     barrier, max_over_ranks = rk.barrier, rk.max_over_ranks
 
-    CODEC = {"lz4": c.CODEC_LZ4BLOCK, "snappy": c.CODEC_SNAPPY_XERIAL, "zstd": c.CODEC_ZSTD}[args.codec]
+    CODEC = {"lz4": c.CODEC_LZ4BLOCK, "snappy": c.CODEC_SNAPPY_XERIAL, "zstd": c.CODEC_ZSTD}[codec_name]
+    LEVEL = 3 if codec_name == "zstd" else 0
     cmp_cap = int(c.compress_bound(CODEC, LZ4_BLOCK, block_bytes)) * n
-    d_src, d_cmp, d_out = c.dev_alloc(total), c.dev_alloc(cmp_cap), c.dev_alloc(total)
-    c.gen_terasort_dev(d_src, rank * n * RECORDS_PER_BLOCK, n * RECORDS_PER_BLOCK, 42)
+    d_src, d_cmp, d_out = c.dev_alloc(wave_bytes), c.dev_alloc(cmp_cap), c.dev_alloc(wave_bytes)
+    c.gen_terasort_dev(d_src, rank * n * rpb, n * rpb, 42)
     off = np.arange(n, dtype=np.uint64) * block_bytes
     ln = np.full(n, block_bytes, dtype=np.uint64)
     sb = np.arange(n + 1, dtype=np.uint32)
@@ -207,10 +273,10 @@ def main():
     kt = {"write_kernel_ms": [], "read_kernel_ms": [], "compress_ms": [], "decompress_ms": [], "match_ms": [],
           "match_launches": []}
 
-    def step_device(record):
-        w = c.compress_dev(CODEC, d_src, off, ln, d_cmp, cmp_cap, LZ4_BLOCK, c.CHECKSUM_CRC32C)
+    def wave_device(record):
+        w = c.compress_dev(CODEC, d_src, off, ln, d_cmp, cmp_cap, LZ4_BLOCK, c.CHECKSUM_CRC32C, level=LEVEL)
         tw = c.last_timing()
-        r = c.decompress_dev(CODEC, d_cmp, w["dst_off"], w["dst_len"], d_out, total, c.CHECKSUM_CRC32C, sb,
+        r = c.decompress_dev(CODEC, d_cmp, w["dst_off"], w["dst_len"], d_out, wave_bytes, c.CHECKSUM_CRC32C, sb,
                              w["dst_len"], w["checksums"])
         tr = c.last_timing()
         if record:
@@ -219,13 +285,18 @@ def main():
             kt["read_kernel_ms"].append(tr["kernel_ms"]); kt["decompress_ms"].append(tr["top_kernel_ms"])
         return w, r
 
+    def step_device(record):
+        for _ in range(waves):
+            w, r = wave_device(record)
+        return w, r
+
     want = c.checksum_dev(c.CHECKSUM_CRC32C, d_src, off, ln)
     for _ in range(warmup):
         w, r = step_device(False)
-    assert not w["status"].any() and not r["status"].any() and r["total"] == total, "device round trip failed"
+    assert not w["status"].any() and not r["status"].any() and r["total"] == wave_bytes, "device round trip failed"
     got = c.checksum_dev(c.CHECKSUM_CRC32C, d_out, off, ln)
     assert (got == want).all(), "decode(encode(x)) != x"
-    ratio = w["total"] / total
+    ratio = w["total"] / wave_bytes
 
     sampler = ClockSampler(local_rank)
     launches0 = L.b2s_total_kernel_launches()
@@ -243,48 +314,51 @@ def main():
     clocks = sampler.stop()
     launches = L.b2s_total_kernel_launches() - launches0
     ms_per_step = elapsed / steps * 1e3
-    value = world * total / (elapsed / steps) / 1e9
+    value = world * rank_bytes / (elapsed / steps) / 1e9
 
-    comp_ms = statistics.mean(kt["compress_ms"])
+    comp_ms = statistics.mean(kt["compress_ms"])          # per wave
     match_ms = statistics.mean(kt["match_ms"])
     match_launches = max(1, int(statistics.mean(kt["match_launches"])))
+    dec_ms = statistics.mean(kt["decompress_ms"])
     peak, peak_src = measured_peak()
-    # dominant kernel = lz4_match_kernel (phase A of the compressor; largest share in profiles/*launches*.csv).
+    pipe = int(os.environ.get("B2S_LZ4_PIPE", "2"))
+    dom_kernel = "lz4_match2_kernel<12>" if pipe != 1 else "lz4_match_kernel<12>"
+    # dominant kernel = the match kernel (phase A of the compressor; largest share in profiles/*launches*.csv).
     # achieved = SURVEY §8(d)'s write-step figure (1+r) x the input bytes one launch processes / its launch duration.
-    step_alg = (1.0 + ratio) * total                       # compress step reads U, writes C (= decompress step mirrored)
+    step_alg = (1.0 + ratio) * wave_bytes                  # compress step reads U, writes C (= decompress step mirrored)
     alg_bytes = step_alg / match_launches
     achieved = alg_bytes / (match_ms / match_launches * 1e-3) / 1e9
-    dec_ms = statistics.mean(kt["decompress_ms"])
-    roofline = {"bound": "hbm", "kernel": "lz4_match_kernel<12>", "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": NCU_TRAFFIC_PER_LAUNCH,
+    codec_blocks_per_launch = n * -(-block_bytes // LZ4_BLOCK) / match_launches
+    roofline = {"bound": "hbm", "kernel": dom_kernel, "achieved": round(achieved, 2), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 5),
+                "traffic": int(NCU_TRAFFIC_PER_CODEC_BLOCK * codec_blocks_per_launch) if pipe != 1 else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(match_ms / match_launches, 4),
-                "launches_per_step": match_launches,
-                "compress_step": {"kernels": "lz4_match + lz4_parse + scan + lz4_emit (what one fused kernel would do)",
+                "launches_per_wave": match_launches,
+                "compress_step": {"kernels": "match + parse + scan + emit (what one fused kernel would do)",
                                   "algorithmic_bytes": int(step_alg), "ms": round(comp_ms, 3),
                                   "achieved": round(step_alg / (comp_ms * 1e-3) / 1e9, 2),
                                   "frac": round(step_alg / (comp_ms * 1e-3) / 1e9 / peak, 5)},
-                "decompress_step": {"kernels": "lz4_tokens + lz4_copy", "algorithmic_bytes": int(step_alg),
+                "decompress_step": {"kernels": "tokens + copy", "algorithmic_bytes": int(step_alg),
                                     "ms": round(dec_ms, 3), "achieved": round(step_alg / (dec_ms * 1e-3) / 1e9, 2),
                                     "frac": round(step_alg / (dec_ms * 1e-3) / 1e9 / peak, 5)},
                 "note": "LZ77 coding is issue/latency-bound byte-stream work; traffic (ncu dram bytes per launch, "
-                        "profiles/) exceeds the algorithmic bytes by the per-position match table handed to the parse kernel"}
-    kernels = {"compress_ms": round(comp_ms, 3), "match_ms": round(match_ms, 3), "decompress_ms": round(statistics.mean(kt["decompress_ms"]), 3),
+                        "profiles/) exceeds the algorithmic bytes by the per-position off[] table handed to the parse kernel"}
+    kernels = {"per": "wave", "compress_ms": round(comp_ms, 3), "match_ms": round(match_ms, 3), "decompress_ms": round(dec_ms, 3),
                "write_pass_kernels_ms": round(statistics.mean(kt["write_kernel_ms"]), 3),
                "read_pass_kernels_ms": round(statistics.mean(kt["read_kernel_ms"]), 3),
-               "compress_GBps_uncompressed": round(total / comp_ms / 1e6, 2),
-               "decompress_GBps_uncompressed": round(total / statistics.mean(kt["decompress_ms"]) / 1e6, 2)}
+               "compress_GBps_uncompressed": round(wave_bytes / comp_ms / 1e6, 2),
+               "decompress_GBps_uncompressed": round(wave_bytes / dec_ms / 1e6, 2)}
 
     # ------------------------------------------------------------------ e2e through the host-pointer C ABI
     e2e = None
     if not args.no_e2e:
-        # pinned host arenas: 3 x ~10 GiB per rank.  If any rank cannot get them (host RAM at N=8), every rank falls
-        # back together to a quarter of the blocks — and the line says so — instead of one rank dying at a barrier.
-        def alloc(nblk):
+        # pinned host arenas (NUMA-local: b2s_host_alloc places them next to the rank's GPU): source, compressed (write
+        # side), compressed copy (read side's input while the write side overwrites its own), decoded
+        def alloc():
             bufs = []
             try:
-                for nbytes in (nblk * block_bytes, int(c.compress_bound(CODEC, LZ4_BLOCK, block_bytes)) * nblk,
-                               nblk * block_bytes):
+                for nbytes in (wave_bytes, cmp_cap, cmp_cap, wave_bytes):
                     bufs.append(c.HostBuffer(nbytes))
                 return bufs
             except Exception:
@@ -292,73 +366,115 @@ def main():
                     hb.free()
                 return None
 
-        n_e = n
-        bufs = alloc(n_e)
-        if max_over_ranks(0.0 if bufs is not None else 1.0) > 0:
-            if bufs is not None:
-                for hb in bufs:
-                    hb.free()
-            n_e = max(1, n // 4)
-            bufs = alloc(n_e)
+        bufs = alloc()
         if max_over_ranks(0.0 if bufs is not None else 1.0) > 0:
             if bufs is not None:
                 for hb in bufs:
                     hb.free()
             e2e = {"value": None, "unit": "GB/s", "error": "pinned host memory for the end-to-end leg could not be allocated"}
         else:
-            h_src, h_cmp, h_out = bufs
-            total_e = n_e * block_bytes
-            off_e, ln_e, sb_e = off[:n_e], ln[:n_e], sb[: n_e + 1]
-            c.dev_memcpy(h_src.ptr, d_src, total_e, 2)
+            h_src, h_cmp, h_cmp_in, h_out = bufs
+            c.dev_memcpy(h_src.ptr, d_src, wave_bytes, 2)
             for p in (d_src, d_cmp, d_out):
                 c.dev_free(p)
             d_src = d_cmp = d_out = None
 
-            def step_host():
-                w = c.compress_packed(CODEC, h_src.array, off_e, ln_e, h_cmp.array, LZ4_BLOCK, c.CHECKSUM_CRC32C)
-                tw = c.last_timing()
-                r = c.decompress_packed(CODEC, h_cmp.array, w["dst_off"], w["dst_len"], h_out.array,
-                                        c.CHECKSUM_CRC32C, sb_e, w["dst_len"], w["checksums"])
-                tr = c.last_timing()
-                return w, r, tw, tr
+            def write_pass():
+                w = c.compress_packed(CODEC, h_src.array, off, ln, h_cmp.array, LZ4_BLOCK, c.CHECKSUM_CRC32C, level=LEVEL)
+                return w, c.last_timing()
 
-            w, r, tw, tr = step_host()   # warm-up (allocates slot buffers)
-            assert not w["status"].any() and not r["status"].any() and r["total"] == total_e
-            for i in (0, n_e // 2, n_e - 1):
+            def read_pass(w, src):
+                r = c.decompress_packed(CODEC, src.array, w["dst_off"], w["dst_len"], h_out.array,
+                                        c.CHECKSUM_CRC32C, sb, w["dst_len"], w["checksums"])
+                return r, c.last_timing()
+
+            w, tw = write_pass()   # warm-up (allocates slot buffers)
+            r, tr = read_pass(w, h_cmp)
+            assert not w["status"].any() and not r["status"].any() and r["total"] == wave_bytes
+            for i in (0, n // 2, n - 1):
                 a = h_src.array[i * block_bytes:(i + 1) * block_bytes]
                 b = h_out.array[int(r["dst_off"][i]):int(r["dst_off"][i]) + block_bytes]
                 assert np.array_equal(a, b), "e2e round trip mismatch"
-            step_host()
+            h_cmp_in.array[: w["total"]] = h_cmp.array[: w["total"]]
+            w0 = w
+
+            # ---- serial: one call at a time (write pass, then read pass)
+            write_pass(); read_pass(w0, h_cmp)
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
-                w, r, tw, tr = step_host()
+                for _ in range(waves):
+                    w, tw = write_pass()
+                    r, tr = read_pass(w, h_cmp)
             barrier()
-            e_elapsed = max_over_ranks(time.perf_counter() - t0)
-            e_val = world * total_e / (e_elapsed / args.e2e_steps) / 1e9
-            e2e = {"value": round(e_val, 3), "unit": "GB/s",
-                   "h2d_bytes_per_step": int(tw["h2d_bytes"] + tr["h2d_bytes"]),
-                   "d2h_bytes_per_step": int(tw["d2h_bytes"] + tr["d2h_bytes"]),
-                   "ms_per_step": round(e_elapsed / args.e2e_steps * 1e3, 2), "steps": args.e2e_steps,
-                   "blocks_per_gpu": n_e,
-                   "write_ms": round(tw["total_ms"], 2), "read_ms": round(tr["total_ms"], 2),
-                   "write_sums_ms": {k: round(tw[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
-                   "read_sums_ms": {k: round(tr[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
-                   "api": "b2s_compress_packed + b2s_decompress_packed on pinned host arenas (b2s_host_alloc)"}
-            if n_e != n:
-                e2e["note"] = "pinned host memory did not allow the full %d blocks per rank; measured on %d" % (n, n_e)
-            if world == 1 and n_e >= 200:
+            s_elapsed = max_over_ranks(time.perf_counter() - t0)
+            s_val = world * rank_bytes / (s_elapsed / args.e2e_steps) / 1e9
+            serial = {"value": round(s_val, 3), "ms_per_step": round(s_elapsed / args.e2e_steps * 1e3, 2),
+                      "write_ms": round(tw["total_ms"], 2), "read_ms": round(tr["total_ms"], 2),
+                      "write_sums_ms": {k: round(tw[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
+                      "read_sums_ms": {k: round(tr[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")}}
+
+            # ---- write || read: two task threads, one per lane of the ABI (map-side compress of this wave while the
+            # reduce side decodes the previous wave's output), both directions of the link busy
+            errs = []
+            tms = {}
+
+            def writer():
+                try:
+                    c.bind_thread_to_device(0)
+                    for _ in range(args.e2e_steps * waves):
+                        ww, t = write_pass()
+                        assert not ww["status"].any()
+                    tms["w"] = t
+                except Exception as ex:  # noqa: BLE001
+                    errs.append(repr(ex))
+
+            def reader():
+                try:
+                    c.bind_thread_to_device(0)
+                    for _ in range(args.e2e_steps * waves):
+                        rr, t = read_pass(w0, h_cmp_in)
+                        assert not rr["status"].any() and rr["total"] == wave_bytes
+                    tms["r"] = t
+                except Exception as ex:  # noqa: BLE001
+                    errs.append(repr(ex))
+
+            barrier()
+            t0 = time.perf_counter()
+            ths = [threading.Thread(target=writer), threading.Thread(target=reader)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            barrier()
+            c_elapsed = max_over_ranks(time.perf_counter() - t0)
+            if errs:
+                raise RuntimeError("concurrent e2e leg failed: %s" % errs)
+            c_val = world * rank_bytes / (c_elapsed / args.e2e_steps) / 1e9
+            tw2, tr2 = tms["w"], tms["r"]
+            e2e = {"value": round(c_val, 3), "unit": "GB/s", "mode": "write || read: a compress call and a decompress call in "
+                   "flight together from two task threads (one per ABI lane), each over the rank's whole share per step",
+                   "h2d_bytes_per_step": int((tw2["h2d_bytes"] + tr2["h2d_bytes"]) * waves),
+                   "d2h_bytes_per_step": int((tw2["d2h_bytes"] + tr2["d2h_bytes"]) * waves),
+                   "ms_per_step": round(c_elapsed / args.e2e_steps * 1e3, 2), "steps": args.e2e_steps,
+                   "blocks_per_gpu": n * waves, "numa_node": numa_node,
+                   "write_ms": round(tw2["total_ms"], 2), "read_ms": round(tr2["total_ms"], 2),
+                   "write_sums_ms": {k: round(tw2[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
+                   "read_sums_ms": {k: round(tr2[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
+                   "serial": serial,
+                   "api": "b2s_compress_packed + b2s_decompress_packed on NUMA-local pinned host arenas (b2s_host_alloc)"}
+            if world == 1 and n >= 200:
                 # what ONE Spark task hands over: a map task's 200 partitions (commitAllPartitions), a reduce task's
                 # 80 map outputs (S3ShuffleReader.read) — latency of a single synchronous C-ABI call, median of 5
                 tws, trs = [], []
                 for _ in range(6):
                     t = time.perf_counter()
-                    w1 = c.compress_packed(CODEC, h_src.array, off_e[:200], ln_e[:200], h_cmp.array, LZ4_BLOCK,
-                                           c.CHECKSUM_CRC32C)
+                    w1 = c.compress_packed(CODEC, h_src.array, off[:200], ln[:200], h_cmp.array, LZ4_BLOCK,
+                                           c.CHECKSUM_CRC32C, level=LEVEL)
                     tws.append(time.perf_counter() - t)
                     t = time.perf_counter()
                     r1 = c.decompress_packed(CODEC, h_cmp.array, w1["dst_off"][:80], w1["dst_len"][:80], h_out.array,
-                                             c.CHECKSUM_CRC32C, sb_e[:81], w1["dst_len"][:80], w1["checksums"][:80])
+                                             c.CHECKSUM_CRC32C, sb[:81], w1["dst_len"][:80], w1["checksums"][:80])
                     trs.append(time.perf_counter() - t)
                     assert not w1["status"].any() and not r1["status"].any()
                 tw1, tr1 = statistics.median(tws[1:]), statistics.median(trs[1:])
@@ -371,21 +487,22 @@ def main():
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        sample_blocks = min(args.cpu_sample_blocks, n)
-        sample = oracle.gen_terasort(0, sample_blocks * RECORDS_PER_BLOCK)
-        cpu_arm(oracle, sample[: 200 * block_bytes], block_bytes, threads)
-        v, detail = cpu_arm(oracle, sample, block_bytes, threads, repeats=2)
-        v1, _ = cpu_arm(oracle, sample[: 64 * block_bytes], block_bytes, 1)
-        cpu = {"value": round(v, 3), "unit": "GB/s", "cores": threads, "kind": "port",
+        threads, aff, quota = usable_cores()
+        sample_blocks = max(1, min(args.cpu_sample_bytes // block_bytes, n))
+        sample = oracle.gen_terasort(0, sample_blocks * rpb)
+        cpu_arm(oracle, codec_name, sample[: min(200, sample_blocks) * block_bytes], block_bytes, threads)
+        v, detail = cpu_arm(oracle, codec_name, sample, block_bytes, threads, repeats=2)
+        v1, _ = cpu_arm(oracle, codec_name, sample[: min(64, sample_blocks) * block_bytes], block_bytes, 1)
+        cpu = {"value": round(v, 3), "unit": "GB/s", "cores": threads, "affinity_threads": aff, "cgroup_cpu_quota": quota,
+               "kind": "port",
                "sample": "%d of %d shuffle blocks (%.2f GiB), same generator/seed, best of 2" % (
-                   sample_blocks, n, sample.size / 2**30),
+                   sample_blocks, n * waves, sample.size / 2**30),
                "single_core_GBps": round(v1, 3),
-               "note": CPU_NOTES[args.codec]}
+               "note": CPU_NOTES[codec_name]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": steps,
-                "warmup": warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+                "warmup": warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": P["scaling"],
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "compressed_ratio": round(ratio, 4), "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roofline, "kernels": kernels}

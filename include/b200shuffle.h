@@ -64,12 +64,22 @@ extern "C" {
  * their streams round-robin over the selected devices (stream i -> device i mod D), one host thread, pinned staging and
  * streams per device, nothing exchanged between devices.  Packed and device-resident calls run on ONE device: the calling
  * thread's (b2s_set_thread_device, default 0) — an executor pins each task thread to a device, or, as bench.py does,
- * runs one process per GPU.  pinned_bytes_per_gpu / streams_per_gpu are accepted for compatibility; staging and slots
- * are sized automatically.  Idempotent. */
+ * runs one process per GPU.  streams_per_gpu = pipeline slots (stream pair + staging) per lane, 2..8, 0 = default 6;
+ * pinned_bytes_per_gpu = the library's own pinned descriptor blocks are allocated up front from this budget (0 = grow on
+ * demand; payload staging is the caller's, b2s_host_alloc).  Every device runs two LANES — write-side calls take one,
+ * read-side calls the other — so a compress and a decompress call from different threads overlap on the full-duplex
+ * link.  Idempotent. */
 int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_per_gpu);
 void b2s_shutdown(void);
 int b2s_device_count(void); /* devices selected by b2s_init, or B2S_E_NOT_INIT */
 int b2s_set_thread_device(uint32_t dev_index); /* device used by this thread's packed / host-pointer calls */
+/* NUMA placement (SURVEY.md §8e "NUMA-pin staging buffers to the GPU's socket"; the reference's task threads are the
+ * ones of storage/S3BufferedPrefetchIterator.scala:78-92 and the map task).  b2s_bind_thread_to_device = set_thread_device
+ * + pin the calling thread to the CPUs of the device's NUMA node + prefer that node for its allocations (best effort;
+ * a no-op returning 0 when the topology is unknown or B2S_NUMA=0).  b2s_host_alloc always places its pages next to the
+ * calling thread's device.  b2s_device_numa_node: the node, -1000 if unknown. */
+int b2s_bind_thread_to_device(uint32_t dev_index);
+int b2s_device_numa_node(uint32_t dev_index);
 const char* b2s_strerror(int32_t code);
 const char* b2s_last_error(void); /* thread-local text of the last B2S_E_CUDA / B2S_E_ARG */
 uint32_t b2s_version(void);

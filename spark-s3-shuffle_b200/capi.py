@@ -38,6 +38,8 @@ PROTOTYPES = [
     ("b2s_shutdown", None, []),
     ("b2s_device_count", C.c_int, []),
     ("b2s_set_thread_device", C.c_int, [_u32]),
+    ("b2s_bind_thread_to_device", C.c_int, [_u32]),
+    ("b2s_device_numa_node", C.c_int, [_u32]),
     ("b2s_strerror", C.c_char_p, [_i32]),
     ("b2s_last_error", C.c_char_p, []),
     ("b2s_version", _u32, []),
@@ -107,6 +109,12 @@ def _check(rc, where):
 
 def init(gpu_mask=0, pinned_bytes_per_gpu=0, streams_per_gpu=0):
     _check(load().b2s_init(gpu_mask, pinned_bytes_per_gpu, streams_per_gpu), "b2s_init")
+
+
+def bind_thread_to_device(dev=0):
+    """pins the calling thread to the CPUs of the device's NUMA node and prefers that node for its allocations"""
+    _check(load().b2s_bind_thread_to_device(dev), "b2s_bind_thread_to_device")
+    return load().b2s_device_numa_node(dev)
 
 
 def shutdown():

@@ -18,6 +18,10 @@
 #include <thread>
 #include <vector>
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "kernels.h"
 
 using namespace b2s;
@@ -44,7 +48,8 @@ int fail_cuda(const char* what, cudaError_t e) {
     if (e__ != cudaSuccess) return fail_cuda(#call, e__);  \
   } while (0)
 
-constexpr int NSLOT = 6;
+constexpr int NSLOT = 8;  // upper bound; g_nslot (b2s_init streams_per_gpu, default 6) are used
+int g_nslot = 6;
 uint64_t g_host_chunk_bytes = 256ull << 20;  // host-pointer calls: bytes per pipeline chunk (B2S_HOST_CHUNK_MB).  The thread-per-block
                                               // kernels cost ~2 ms per launch whatever the block count, so chunks must be large enough to amortise them
 constexpr uint32_t kChunkStreams = 1u << 18;
@@ -55,6 +60,85 @@ int g_lz4d_legacy = 0;
 int g_trace = 0;  // B2S_TRACE=1: per-chunk timeline of the compress pipeline on stderr  // B2S_LZ4D_LEGACY=1: single-kernel tile decoder for every block size (A/B comparisons)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// --------------------------------------------------------------------------------------------------------------
+// NUMA placement of pinned staging ("NUMA-pin staging buffers to the GPU's socket").  On the 8-GPU boxes
+// GPUs 0-3 hang off socket 0 and 4-7 off socket 1; pinned arenas that land on the other socket send every H2D/D2H
+// byte across the socket interconnect, which is what capped the host-staged path at 4 and 8 ranks.
+// Raw syscalls (no libnuma in the image).  B2S_NUMA=0 disables all of it.
+// --------------------------------------------------------------------------------------------------------------
+int g_numa = 1;
+namespace numa {
+constexpr int kDefault = 0, kPreferred = 1;
+constexpr unsigned long kMaskBits = 1024;
+struct Mask {
+  unsigned long w[kMaskBits / (8 * sizeof(unsigned long))] = {};
+};
+inline long set_policy(int mode, const Mask* m) {
+  return syscall(SYS_set_mempolicy, mode, m ? m->w : nullptr, m ? kMaskBits + 1 : 0ul);
+}
+inline long get_policy(int* mode, Mask* m) {
+  return syscall(SYS_get_mempolicy, mode, m->w, kMaskBits + 1, nullptr, 0ul);
+}
+int node_of_pci(const char* busid) {  // "0000:40:00.0" -> /sys/bus/pci/devices/0000:40:00.0/numa_node
+  char path[256], low[64];
+  size_t k = 0;
+  for (; busid[k] && k + 1 < sizeof low; k++) low[k] = (char)((busid[k] >= 'A' && busid[k] <= 'F') ? busid[k] + 32 : busid[k]);
+  low[k] = 0;
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", low);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+bool node_cpus(int node, cpu_set_t* set) {  // parses /sys/devices/system/node/nodeN/cpulist ("0-31,64-95")
+  char path[128], buf[4096];
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  const bool got = fgets(buf, sizeof buf, f) != nullptr;
+  fclose(f);
+  if (!got) return false;
+  CPU_ZERO(set);
+  int count = 0;
+  for (char* q = buf; *q && *q != '\n';) {
+    char* e = nullptr;
+    long a = strtol(q, &e, 10), b = a;
+    if (e == q) break;
+    q = e;
+    if (*q == '-') {
+      b = strtol(q + 1, &e, 10);
+      q = e;
+    }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++) {
+      CPU_SET((int)c, set);
+      count++;
+    }
+    if (*q == ',') q++;
+  }
+  return count > 0;
+}
+// allocations made while one of these is alive come from `node` when it has room (MPOL_PREFERRED); the thread's
+// previous policy is put back afterwards
+struct PreferNode {
+  bool active = false;
+  int old_mode = 0;
+  Mask old_mask;
+  explicit PreferNode(int node) {
+    if (!g_numa || node < 0 || node >= (int)kMaskBits) return;
+    if (get_policy(&old_mode, &old_mask) != 0) return;
+    Mask m;
+    m.w[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    active = set_policy(kPreferred, &m) == 0;
+  }
+  ~PreferNode() {
+    if (active) set_policy(old_mode, old_mode == kDefault ? nullptr : &old_mask);
+  }
+};
+}  // namespace numa
+thread_local int t_numa_node = -1;  // node of the device this thread's pinned allocations should sit next to
 
 struct DevBuf {
   void* p = nullptr;
@@ -92,6 +176,7 @@ struct PinBuf {
     p = nullptr;
     cap = 0;
     size_t want = align_up(bytes + bytes / 4, 1 << 16);
+    numa::PreferNode near(t_numa_node);
     cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
     if (e != cudaSuccess) {
       p = nullptr;
@@ -149,13 +234,22 @@ struct Slot {
   }
 };
 
+// A device runs two independent LANES: write-side calls (compress) take lane 0, read-side calls (decompress,
+// checksum) lane 1.  Each lane has its own lock, pipeline slots, streams and staging, so a map task's compress call
+// (H2D-heavy) and a reduce task's decompress call (D2H-heavy) from different threads overlap on the full-duplex PCIe
+// link instead of queueing behind one per-device mutex (the two directions were never busy together).
+constexpr int kLaneWrite = 0, kLaneRead = 1, kLanes = 2;
+struct Lane {
+  Slot slot[NSLOT];
+  std::mutex mtx;
+};
 struct Device {
   int ordinal = 0;
-  Slot slot[NSLOT];
+  int numa_node = -1;            // /sys/bus/pci/devices/<bdf>/numa_node, -1 = unknown
+  Lane lane[kLanes];
   ChecksumTables tabs{};
   void* zstd_ctables = nullptr;  // predefined FSE compression tables (zstd_enc.cu)
   cudaEvent_t ev_mark[2] = {nullptr, nullptr};  // b2s_mark stopwatch
-  std::mutex mtx;
 };
 
 struct Context {
@@ -608,6 +702,7 @@ int get_device(uint32_t dev_index, Device** out) {
   if (!g_ctx) return fail(B2S_E_NOT_INIT, "b2s_init has not been called%s");
   if (dev_index >= g_ctx->devs.size()) return fail(B2S_E_ARG, "device index out of range%s");
   *out = g_ctx->devs[dev_index];
+  t_numa_node = (*out)->numa_node;
   CU(cudaSetDevice((*out)->ordinal));
   return 0;
 }
@@ -755,8 +850,6 @@ const char* b2s_strerror(int32_t code) {
 const char* b2s_last_error(void) { return t_last_error.c_str(); }
 
 int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_per_gpu) {
-  (void)pinned_bytes_per_gpu;
-  (void)streams_per_gpu;
   std::lock_guard<std::mutex> lk(g_init_mtx);
   if (g_ctx) return 0;
   int count = 0;
@@ -765,26 +858,41 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
     return fail(B2S_E_CUDA, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
   g_lz4_hlog = env_int("B2S_LZ4_HLOG", g_lz4_hlog);
   g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
+  g_lz4_pipe = env_int("B2S_LZ4_PIPE", g_lz4_pipe);
   g_lz4_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4_CHUNK_BLOCKS", (int)g_lz4_chunk_blocks));
   g_lz4d_legacy = env_int("B2S_LZ4D_LEGACY", 0);
   g_trace = env_int("B2S_TRACE", 0);
+  g_numa = env_int("B2S_NUMA", 1);
   g_lz4d_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4D_CHUNK_BLOCKS", (int)g_lz4d_chunk_blocks));
   g_host_chunk_bytes = (uint64_t)std::max(1, env_int("B2S_HOST_CHUNK_MB", (int)(g_host_chunk_bytes >> 20))) << 20;
+  // streams_per_gpu: pipeline slots (stream pairs + staging) per lane, 0 = default; B2S_SLOTS overrides
+  g_nslot = std::min(NSLOT, std::max(2, env_int("B2S_SLOTS", streams_per_gpu ? (int)streams_per_gpu : g_nslot)));
   Context* C = new Context();
   for (int d = 0; d < count && d < 32; d++) {
     if (gpu_mask && !(gpu_mask & (1u << d))) continue;
     CU(cudaSetDevice(d));
     Device* D = new Device();
     D->ordinal = d;
-    for (int k = 0; k < NSLOT; k++) {
-      Slot& S = D->slot[k];
-      CU(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
-      CU(cudaStreamCreateWithFlags(&S.st2, cudaStreamNonBlocking));
-      cudaEvent_t* evs2[] = {&S.ev_fork, &S.ev_match[0], &S.ev_match[1], &S.ev_free[0], &S.ev_free[1]};
-      for (auto p : evs2) CU(cudaEventCreateWithFlags(p, cudaEventDisableTiming));
-      cudaEvent_t* evs[] = {&S.ev_a, &S.ev_b, &S.ev_k0, &S.ev_k1, &S.ev_t0, &S.ev_t1, &S.ev_h0, &S.ev_h1, &S.ev_d0, &S.ev_d1};
-      for (auto p : evs) CU(cudaEventCreate(p));
-    }
+    char busid[32] = {0};
+    if (g_numa && cudaDeviceGetPCIBusId(busid, sizeof busid, d) == cudaSuccess) D->numa_node = numa::node_of_pci(busid);
+    (void)cudaGetLastError();
+    t_numa_node = D->numa_node;
+    for (int l = 0; l < kLanes; l++)
+      for (int k = 0; k < g_nslot; k++) {
+        Slot& S = D->lane[l].slot[k];
+        CU(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&S.st2, cudaStreamNonBlocking));
+        cudaEvent_t* evs2[] = {&S.ev_fork, &S.ev_match[0], &S.ev_match[1], &S.ev_free[0], &S.ev_free[1]};
+        for (auto p : evs2) CU(cudaEventCreateWithFlags(p, cudaEventDisableTiming));
+        cudaEvent_t* evs[] = {&S.ev_a, &S.ev_b, &S.ev_k0, &S.ev_k1, &S.ev_t0, &S.ev_t1, &S.ev_h0, &S.ev_h1, &S.ev_d0, &S.ev_d1};
+        for (auto p : evs) CU(cudaEventCreate(p));
+        // pinned_bytes_per_gpu: the library's own pinned descriptor blocks are sized up front (split over the slots)
+        // instead of growing on first use; 0 = grow on demand.  Payload staging is the caller's (b2s_host_alloc).
+        if (pinned_bytes_per_gpu) {
+          const uint64_t per = std::min<uint64_t>(pinned_bytes_per_gpu / (uint64_t)(kLanes * g_nslot), 64ull << 20);
+          if (per >= 4096 && S.hmeta.ensure(per)) return B2S_E_NOMEM;
+        }
+      }
     if (checksum_tables_create(&D->tabs)) return fail(B2S_E_CUDA, "checksum table upload failed%s");
     if (zstd_ctables_create(&D->zstd_ctables)) return fail(B2S_E_CUDA, "zstd table upload failed%s");
     zstd_set_ctables(d, D->zstd_ctables);
@@ -796,6 +904,7 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
     delete C;
     return fail(B2S_E_ARG, "gpu_mask selects no visible device%s");
   }
+  t_numa_node = C->devs[0]->numa_node;
   g_ctx = C;
   return 0;
 }
@@ -806,8 +915,9 @@ void b2s_shutdown(void) {
   for (Device* D : g_ctx->devs) {
     cudaSetDevice(D->ordinal);
     cudaDeviceSynchronize();
+    for (int l = 0; l < kLanes; l++)
     for (int k = 0; k < NSLOT; k++) {
-      Slot& S = D->slot[k];
+      Slot& S = D->lane[l].slot[k];
       S.meta.release();
       S.scratch.release();
       S.desc.release();
@@ -842,11 +952,33 @@ int b2s_set_thread_device(uint32_t dev_index) {
   if (!g_ctx) return fail(B2S_E_NOT_INIT, "b2s_init has not been called%s");
   if (dev_index >= g_ctx->devs.size()) return fail(B2S_E_ARG, "device index out of range%s");
   t_device = dev_index;
+  t_numa_node = g_ctx->devs[dev_index]->numa_node;
   return 0;
+}
+
+int b2s_bind_thread_to_device(uint32_t dev_index) {
+  int rc = b2s_set_thread_device(dev_index);
+  if (rc) return rc;
+  const int node = g_ctx->devs[dev_index]->numa_node;
+  if (!g_numa || node < 0) return 0;  // topology unknown (or B2S_NUMA=0): nothing to do, not an error
+  cpu_set_t set;
+  if (numa::node_cpus(node, &set)) sched_setaffinity(0, sizeof set, &set);  // best effort: a cpuset cgroup may refuse
+  numa::Mask m;
+  m.w[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+  numa::set_policy(numa::kPreferred, &m);
+  return 0;
+}
+int b2s_device_numa_node(uint32_t dev_index) {
+  if (!g_ctx) return B2S_E_NOT_INIT;
+  if (dev_index >= g_ctx->devs.size()) return B2S_E_ARG;
+  return g_ctx->devs[dev_index]->numa_node < 0 ? -1000 : g_ctx->devs[dev_index]->numa_node;
 }
 
 void* b2s_host_alloc(uint64_t bytes) {
   void* p = nullptr;
+  // next to the calling thread's device (b2s_set_thread_device / b2s_bind_thread_to_device; device 0 by default)
+  if (g_ctx && t_device < g_ctx->devs.size()) t_numa_node = g_ctx->devs[t_device]->numa_node;
+  numa::PreferNode near(t_numa_node);
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
     fail(B2S_E_NOMEM, "cudaHostAlloc failed%s");
     return nullptr;
@@ -914,7 +1046,7 @@ int b2s_mark(uint32_t dev_index, uint32_t which) {
   if (rc) return rc;
   if (which > 1) return fail(B2S_E_ARG, "mark index must be 0 or 1%s");
   // every entry point is synchronous, so an event on the first slot's stream brackets whatever ran in between
-  CU(cudaEventRecord(D->ev_mark[which], D->slot[0].st));
+  CU(cudaEventRecord(D->ev_mark[which], D->lane[kLaneWrite].slot[0].st));
   return 0;
 }
 int b2s_marks_elapsed_ms(uint32_t dev_index, double* ms) {
@@ -933,9 +1065,10 @@ int b2s_gen_terasort_dev(uint32_t dev_index, void* d_dst, uint64_t first_record,
   Device* D;
   int rc = get_device(dev_index, &D);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(D->mtx);
-  launch_gen_terasort((uint8_t*)d_dst, first_record, n_records, seed, D->slot[0].st);
-  CU(cudaStreamSynchronize(D->slot[0].st));
+  Lane& Ln = D->lane[kLaneWrite];
+  std::lock_guard<std::mutex> lk(Ln.mtx);
+  launch_gen_terasort((uint8_t*)d_dst, first_record, n_records, seed, Ln.slot[0].st);
+  CU(cudaStreamSynchronize(Ln.slot[0].st));
   CU(cudaGetLastError());
   return 0;
 }
@@ -989,12 +1122,13 @@ int b2s_checksum_dev(uint32_t dev_index, uint32_t alg, uint32_t n, const void* d
   int rc = get_device(dev_index, &D);
   if (rc) return rc;
   if (!n) return 0;
-  std::lock_guard<std::mutex> lk(D->mtx);
+  Lane& Ln = D->lane[kLaneRead];
+  std::lock_guard<std::mutex> lk(Ln.mtx);
   uint64_t total = 0, launches = 0;
   for (uint32_t i = 0; i < n; i++) total += len[i];
-  rc = checksum_chunk_dev(D, D->slot[0], alg, n, (const uint8_t*)d_base, off, len, out, total, &launches);
+  rc = checksum_chunk_dev(D, Ln.slot[0], alg, n, (const uint8_t*)d_base, off, len, out, total, &launches);
   if (rc) return rc;
-  add_timing(D->slot[0], false);
+  add_timing(Ln.slot[0], false);
   t_timing.kernel_launches = launches;
   t_timing.src_bytes = total;
   t_timing.total_ms = wt.ms();
@@ -1009,14 +1143,15 @@ static int checksum_host(uint32_t alg, uint32_t n, const uint8_t* const* ptr, co
   int rc = get_device(t_device, &D);
   if (rc) return rc;
   if (!n) return 0;
-  std::lock_guard<std::mutex> lk(D->mtx);
+  Lane& Ln = D->lane[kLaneRead];
+  std::lock_guard<std::mutex> lk(Ln.mtx);
   std::vector<uint32_t> starts;
   make_chunks(n, len, starts);
   std::vector<uint64_t> dev_off;
   std::vector<Run> runs;
   uint64_t launches = 0;
   for (size_t c = 0; c + 1 < starts.size(); c++) {
-    Slot& S = D->slot[0];
+    Slot& S = Ln.slot[0];
     const uint32_t i0 = starts[c], cnt = starts[c + 1] - starts[c];
     dev_off.resize(cnt);
     uint64_t bytes = plan_runs(cnt, ptr + i0, len + i0, dev_off.data(), runs);
@@ -1084,8 +1219,9 @@ int b2s_compress_dev(uint32_t dev_index, uint32_t codec, int32_t level, uint32_t
   if (dst_total) *dst_total = 0;
   if (!n) return 0;
   if (!src_off || !src_len || !dst_off || !dst_len || !status) return fail(B2S_E_ARG, "null argument%s");
-  std::lock_guard<std::mutex> lk(D->mtx);
-  Slot& S = D->slot[0];
+  Lane& Ln = D->lane[kLaneWrite];
+  std::lock_guard<std::mutex> lk(Ln.mtx);
+  Slot& S = Ln.slot[0];
   const uint32_t bs = block_size_or_default(codec, codec_block_size);
   CompressJob J;
   rc = compress_prepare(S, codec, bs, n, src_len, J);
@@ -1131,17 +1267,18 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
   if (alg > B2S_CHECKSUM_CRC32C) return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
   if (dst_total) *dst_total = 0;
   if (!n) return 0;
-  std::lock_guard<std::mutex> lk(D->mtx);
+  Lane& Ln = D->lane[kLaneWrite];
+  std::lock_guard<std::mutex> lk(Ln.mtx);
   const uint32_t bs = block_size_or_default(codec, codec_block_size);
   std::vector<uint32_t> starts;
   make_chunks(n, src_len, starts);
   const size_t nchunks = starts.size() - 1;
   std::vector<CompressJob> jobs(nchunks);
-  std::vector<std::vector<Run>> runs(NSLOT);
+  std::vector<std::vector<Run>> runs(g_nslot);
   uint64_t launches = 0, run_off = 0;
 
   auto finish = [&](size_t c) -> int {
-    Slot& S = D->slot[c % NSLOT];
+    Slot& S = Ln.slot[c % g_nslot];
     CompressJob& J = jobs[c];
     const uint32_t i0 = starts[c];
     CU(cudaEventSynchronize(S.ev_a));
@@ -1188,9 +1325,9 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
   };
 
   for (size_t c = 0; c < nchunks; c++) {
-    Slot& S = D->slot[c % NSLOT];
-    if (c >= NSLOT) {
-      rc = finish(c - NSLOT);
+    Slot& S = Ln.slot[c % g_nslot];
+    if (c >= (size_t)g_nslot) {
+      rc = finish(c - g_nslot);
       if (rc) return rc;
       CU(cudaStreamSynchronize(S.st));  // payload of the slot's previous chunk has left the device
       t_timing.d2h_ms += ms_between(S.ev_d0, S.ev_d1);
@@ -1200,7 +1337,7 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
     rc = compress_prepare(S, codec, bs, cnt, src_len + i0, J);
     if (rc) return rc;
     memcpy(J.h_src_len, src_len + i0, (size_t)cnt * 8);
-    uint64_t bytes = plan_runs(cnt, src + i0, src_len + i0, J.h_src_off, runs[c % NSLOT]);
+    uint64_t bytes = plan_runs(cnt, src + i0, src_len + i0, J.h_src_off, runs[c % g_nslot]);
     rc = S.src.ensure(bytes + 64);
     if (rc) return rc;
     uint64_t bound = 0;
@@ -1208,7 +1345,7 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
     rc = S.dst.ensure(bound + 64);
     if (rc) return rc;
     CU(cudaEventRecord(S.ev_h0, S.st));
-    for (const Run& r : runs[c % NSLOT])
+    for (const Run& r : runs[c % g_nslot])
       CU(cudaMemcpyAsync((uint8_t*)S.src.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, S.st));
     CU(cudaEventRecord(S.ev_h1, S.st));
     t_timing.h2d_bytes += bytes;
@@ -1218,13 +1355,13 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
                           &launches);
     if (rc) return rc;
   }
-  for (size_t c = nchunks > NSLOT ? nchunks - NSLOT : 0; c < nchunks; c++) {
+  for (size_t c = nchunks > (size_t)g_nslot ? nchunks - g_nslot : 0; c < nchunks; c++) {
     rc = finish(c);
     if (rc) return rc;
   }
-  for (int k = 0; k < NSLOT; k++) {
-    CU(cudaStreamSynchronize(D->slot[k].st));
-    if ((size_t)k < nchunks) t_timing.d2h_ms += ms_between(D->slot[k].ev_d0, D->slot[k].ev_d1);
+  for (int k = 0; k < g_nslot; k++) {
+    CU(cudaStreamSynchronize(Ln.slot[k].st));
+    if ((size_t)k < nchunks) t_timing.d2h_ms += ms_between(Ln.slot[k].ev_d0, Ln.slot[k].ev_d1);
   }
   CU(cudaGetLastError());
   if (dst_total) *dst_total = run_off;
@@ -1332,8 +1469,9 @@ int b2s_decompress_dev(uint32_t dev_index, uint32_t codec, uint32_t checksum_alg
   if (!src_off || !src_len || !dst_off || !dst_len || !status) return fail(B2S_E_ARG, "null argument%s");
   if (checksum_alg && (!slice_base || !slice_len || !slice_checksum)) return fail(B2S_E_ARG, "slice arrays required%s");
   if (checksum_alg && (rc = check_slices(n, src_len, slice_base, slice_len))) return rc;
-  std::lock_guard<std::mutex> lk(D->mtx);
-  Slot& S = D->slot[0];
+  Lane& Ln = D->lane[kLaneRead];
+  std::lock_guard<std::mutex> lk(Ln.mtx);
+  Slot& S = Ln.slot[0];
   DecompressJob J;
   const uint32_t ns = checksum_alg ? slice_base[n] : 0;
   rc = decompress_prepare(S, codec, checksum_alg, n, ns, J);
@@ -1377,19 +1515,86 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
   if (alg > B2S_CHECKSUM_CRC32C) return fail(B2S_E_UNSUPPORTED, "Unsupported shuffle checksum algorithm%s");
   if (dst_total) *dst_total = 0;
   if (!n) return 0;
-  if (alg && (rc = check_slices(n, src_len, slice_base, slice_len))) return rc;
-  std::lock_guard<std::mutex> lk(D->mtx);
+  if (alg) {
+    // A block whose slices do not tile it (a fetch that came back short: storage/S3ShuffleBlockStream.scala:66-69,88-91
+    // turns I/O errors into a silent EOF) is that block's problem, not the call's: the reference's validation stream
+    // would run out of bytes inside some slice and raise "Invalid checksum detected" for this block only
+    // (storage/S3ChecksumValidationStream.scala:72-74).  Such blocks get B2S_E_CHECKSUM + the slice index and are left
+    // out of the batch; everything else is processed normally.
+    std::vector<uint32_t> good;
+    std::vector<int32_t> where(n, -1);
+    for (uint32_t i = 0; i < n; i++) {
+      if (slice_base[i + 1] < slice_base[i]) return fail(B2S_E_ARG, "slice_base must be non-decreasing%s");
+      uint64_t sum = 0;
+      int32_t first_short = -1;
+      for (uint32_t q = slice_base[i]; q < slice_base[i + 1]; q++) {
+        sum += slice_len[q];
+        if (first_short < 0 && sum > src_len[i]) first_short = (int32_t)(q - slice_base[i]);
+      }
+      if (sum == src_len[i]) good.push_back(i);
+      else where[i] = first_short >= 0 ? first_short : (int32_t)(slice_base[i + 1] - slice_base[i]) - (slice_base[i + 1] > slice_base[i] ? 1 : 0);
+    }
+    if (good.size() != n) {
+      const uint32_t m = (uint32_t)good.size();
+      std::vector<const uint8_t*> sp(m);
+      std::vector<uint64_t> sl(m), dc(m), doff(m), dl(m), l, c;
+      std::vector<uint8_t*> dp(m);
+      std::vector<uint32_t> sb(m + 1, 0);
+      std::vector<int32_t> st(m), bd(m, -1);
+      for (uint32_t k = 0; k < m; k++) {
+        const uint32_t i = good[k];
+        sp[k] = src[i];
+        sl[k] = src_len[i];
+        if (dst) dp[k] = dst[i];
+        if (dst_cap) dc[k] = dst_cap[i];
+        for (uint32_t q = slice_base[i]; q < slice_base[i + 1]; q++) {
+          l.push_back(slice_len[q]);
+          c.push_back(slice_sum[q]);
+        }
+        sb[k + 1] = (uint32_t)l.size();
+      }
+      uint64_t total = 0;
+      const b2s_timing keep = t_timing;
+      rc = m ? decompress_host(codec, alg, m, sp.data(), sl.data(), sb.data(), l.data(), c.data(), packed_dst, packed_cap,
+                               dst ? dp.data() : nullptr, dst_cap ? dc.data() : nullptr, doff.data(), dl.data(), &total,
+                               st.data(), bd.data(), size_only)
+             : 0;
+      if (!m) t_timing = keep;
+      if (rc) return rc;
+      uint32_t k = 0;
+      uint64_t at = 0;
+      for (uint32_t i = 0; i < n; i++) {
+        if (k < m && good[k] == i) {
+          status[i] = st[k];
+          dst_len[i] = dl[k];
+          if (dst_off) dst_off[i] = doff[k];
+          if (bad_slice) bad_slice[i] = bd[k];
+          at = doff[k] + dl[k];
+          k++;
+        } else {
+          status[i] = B2S_E_CHECKSUM;
+          dst_len[i] = 0;
+          if (dst_off) dst_off[i] = at;
+          if (bad_slice) bad_slice[i] = where[i];
+        }
+      }
+      if (dst_total) *dst_total = total;
+      return 0;
+    }
+  }
+  Lane& Ln = D->lane[kLaneRead];
+  std::lock_guard<std::mutex> lk(Ln.mtx);
   std::vector<uint32_t> starts;
   make_chunks(n, src_len, starts);
   const size_t nchunks = starts.size() - 1;
   std::vector<DecompressJob> jobs(nchunks);
   std::vector<uint64_t> chunk_src_bytes(nchunks);
-  std::vector<std::vector<Run>> runs(NSLOT);
+  std::vector<std::vector<Run>> runs(g_nslot);
   uint64_t launches = 0, run_off = 0;
 
   auto stage_a = [&](size_t c) -> int {
-    Slot& S = D->slot[c % NSLOT];
-    if (c >= NSLOT) {
+    Slot& S = Ln.slot[c % g_nslot];
+    if (c >= (size_t)g_nslot) {
       CU(cudaStreamSynchronize(S.st));
       t_timing.d2h_ms += ms_between(S.ev_d0, S.ev_d1);
     }
@@ -1400,13 +1605,13 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
     if (r) return r;
     J.size_only = size_only;
     memcpy(J.h_src_len, src_len + i0, (size_t)cnt * 8);
-    uint64_t bytes = plan_runs(cnt, src + i0, src_len + i0, J.h_src_off, runs[c % NSLOT]);
+    uint64_t bytes = plan_runs(cnt, src + i0, src_len + i0, J.h_src_off, runs[c % g_nslot]);
     chunk_src_bytes[c] = bytes;
     fill_slices(J, i0, cnt, J.h_src_off, src_len, slice_base, slice_len, slice_sum);
     r = S.src.ensure(bytes + 64);
     if (r) return r;
     CU(cudaEventRecord(S.ev_h0, S.st));
-    for (const Run& q : runs[c % NSLOT])
+    for (const Run& q : runs[c % g_nslot])
       CU(cudaMemcpyAsync((uint8_t*)S.src.p + q.dev_off, q.host, q.bytes, cudaMemcpyHostToDevice, S.st));
     CU(cudaEventRecord(S.ev_h1, S.st));
     t_timing.h2d_bytes += bytes;
@@ -1414,7 +1619,7 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
     return decompress_enqueue_a(S, D->tabs, alg, J, (const uint8_t*)S.src.p, bytes, &launches);
   };
   auto stage_b = [&](size_t c) -> int {
-    Slot& S = D->slot[c % NSLOT];
+    Slot& S = Ln.slot[c % g_nslot];
     DecompressJob& J = jobs[c];
     CU(cudaEventSynchronize(S.ev_a));
     if (size_only) {
@@ -1428,7 +1633,7 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
     return decompress_enqueue_b(S, J, (const uint8_t*)S.src.p, (uint8_t*)S.dst.p, S.dst.cap, &launches);
   };
   auto stage_c = [&](size_t c) -> int {
-    Slot& S = D->slot[c % NSLOT];
+    Slot& S = Ln.slot[c % g_nslot];
     DecompressJob& J = jobs[c];
     const uint32_t i0 = starts[c];
     CU(cudaEventSynchronize(S.ev_b));
@@ -1478,9 +1683,9 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
     if (c >= 1 && c - 1 < nchunks && (rc = stage_b(c - 1))) return rc;
     if (c >= 2 && c - 2 < nchunks && (rc = stage_c(c - 2))) return rc;
   }
-  for (int k = 0; k < NSLOT; k++) {
-    CU(cudaStreamSynchronize(D->slot[k].st));
-    if ((size_t)k < nchunks) t_timing.d2h_ms += ms_between(D->slot[k].ev_d0, D->slot[k].ev_d1);
+  for (int k = 0; k < g_nslot; k++) {
+    CU(cudaStreamSynchronize(Ln.slot[k].st));
+    if ((size_t)k < nchunks) t_timing.d2h_ms += ms_between(Ln.slot[k].ev_d0, Ln.slot[k].ev_d1);
   }
   CU(cudaGetLastError());
   if (dst_total) *dst_total = run_off;

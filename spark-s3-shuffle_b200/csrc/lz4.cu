@@ -227,6 +227,10 @@ __global__ void __launch_bounds__(kLz4Threads) lz4_decompress_kernel(const Block
           const int bb = __ldg(in + ip++);
           ll += bb;
           more = (bb == 255);
+          if (ll > olen) {  // cannot be valid, and an unbounded run of 0xFF bytes must not wrap the counter
+            err = true;
+            more = false;
+          }
         }
       }
     }
@@ -263,6 +267,10 @@ __global__ void __launch_bounds__(kLz4Threads) lz4_decompress_kernel(const Block
           const int bb = __ldg(in + ip++);
           ml += bb;
           more = (bb == 255);
+          if (ml > olen) {
+            err = true;
+            more = false;
+          }
         }
       }
     }

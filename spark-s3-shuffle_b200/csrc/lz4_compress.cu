@@ -25,6 +25,7 @@
 // pass so the workspace stays bounded.  Algorithmic bytes stay (1 + r) per input byte; the extra traffic is reported
 // by ncu's dram__bytes (profiles/).
 #include "kernels.h"
+#include "lz4_parse_core.h"
 
 namespace b2s {
 
@@ -407,6 +408,175 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// A2 / B2: the second generation of the match and parse kernels (same specification, same bytes out)
+// ------------------------------------------------------------------------------------------------------------
+// ncu of the first generation (profiles/r1z_final.md): the match kernel is issue bound at 152 warp-instructions per
+// window, and about half of them compute FULL match lengths for all 32 positions (8-byte compares = a third candidate
+// word and a third source word per lane, segment ballots, the cooperative extension loop, the carry) although the
+// greedy parse consults only ~4 positions per window.  Second generation:
+//
+//   A2 lz4_match2_kernel  verifies FOUR bytes and stores off[p] only (2 B per position instead of 4).  The candidate
+//                         and source word pairs already hold the fifth byte, so for codec blocks <= 32 KiB (offsets
+//                         < 2^15) bit 15 of off[p] says "the match is exactly 4 long" — the common case on
+//                         record-shaped data (12 of 14 sequences per terasort record).
+//   B2 lz4_parse2_kernel  still one THREAD per block and a fixed-trip loop, now over groups of FOUR positions (a match
+//                         is >= 4 long: at most one sequence starts per group and its extension starts in the next
+//                         group).  A lane whose match is not flagged "exactly 4" extends it on the source itself, four
+//                         bytes per group, while it walks over the groups the match covers; the candidate words of
+//                         the next group are requested one iteration ahead.  Source and off[] stream through a
+//                         register ring (next trip's loads are issued at the top of the current trip).
+struct Pending2 {
+  uint32_t c0, c1, v, b4, d;  // candidate words, the 4 source bytes, source word holding byte p+4 (pre-shifted), offset (0 = dead)
+  unsigned csh;
+};
+
+template <int HLOG>
+__global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
+    const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
+    const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+    uint32_t stride, uint16_t* __restrict__ offarr, unsigned int* __restrict__ work_counter) {
+  extern __shared__ __align__(16) uint16_t smem_tables[];
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  uint16_t* table = smem_tables + (size_t)(threadIdx.x >> 5) * (1 << HLOG);
+  const int r_me = 31 - lane;  // lane l owns window position 31 - l (see lz4_match_kernel)
+  const bool flag4 = stride <= 32768u;
+
+  for (;;) {
+    uint32_t bl = 0;
+    if (lane == 0) bl = atomicAdd(work_counter, 1u);
+    bl = __shfl_sync(FULL, bl, 0);
+    if (bl >= m) break;
+    const BlockSpan B = block_span(src_base, src_off, src_len, blk_base, n_streams, b0 + bl, block_size);
+    const uint8_t* __restrict__ s = B.s;
+    const int n = B.n;
+    uint16_t* oq = offarr + (size_t)bl * stride + r_me;
+    {
+      uint4* t4 = reinterpret_cast<uint4*>(table);
+      for (int j = lane; j < (1 << HLOG) / 8; j += 32) t4[j] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    if (n < kMFLimit + 1) continue;
+    const int mflimit = n - kMFLimit;
+
+    auto finish = [&](const Pending2& W) {
+      const bool ok = __funnelshift_r(W.c0, W.c1, W.csh) == W.v;
+      uint32_t off = ok ? W.d : 0u;
+      // fifth byte: byte (cand & 3) of c1 against byte (p & 3) of the second source word (b4 is pre-shifted)
+      if (flag4 && off && (((W.c1 >> W.csh) ^ W.b4) & 0xffu)) off |= 0x8000u;
+      __stcs(oq, (uint16_t)off);
+      oq += 32;
+    };
+
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(s + (r_me <= mflimit ? r_me : mflimit));
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0 & ~uintptr_t(3));
+    const unsigned sh = (reinterpret_cast<uintptr_t>(s + r_me) & 3u) * 8u;
+    uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+    uint32_t carry_v = 0;
+    auto step = [&](int pos, Pending2& N, const Pending2& F, bool have_prev) {
+      const bool full = pos + 31 <= mflimit;  // uniform
+      const int p = pos + r_me;
+      const bool valid = p <= mflimit;
+      const int pc = valid ? p : mflimit;
+      uint32_t v, b4;
+      if (full) {
+        v = __funnelshift_r(w0, w1, sh);
+        b4 = w1 >> sh;
+        if (pos + 63 <= mflimit) {  // the next window is full as well: request its words now
+          wp += 8;
+          w0 = __ldg(wp);
+          w1 = __ldg(wp + 1);
+        }
+      } else {  // last, partial window: clamped positions, plain loads (pc + 4 <= n - 8)
+        v = ld32u_ro(s + pc);
+        b4 = __ldg(s + pc + 4);
+      }
+      const uint32_t vprev = __shfl_down_sync(FULL, v, 1);
+      bool rle = vprev == v;
+      if (lane == 31) rle = pos > 0 && carry_v == v;
+      carry_v = __shfl_sync(FULL, v, 0);
+      const uint32_t h = (v * 2654435761u) >> (32 - HLOG);
+      int cand = table[h];
+      if (rle) cand = pc - 1;
+      const bool older = cand < pc;
+      if (!older) cand = 0;  // keep the loads in bounds; the result is discarded
+      {
+        const uintptr_t ca = reinterpret_cast<uintptr_t>(s + cand);
+        const uint32_t* cw = reinterpret_cast<const uint32_t*>(ca & ~uintptr_t(3));
+        N.csh = (ca & 3u) * 8u;
+        N.c0 = __ldg(cw);
+        N.c1 = __ldg(cw + 1);  // covers cand + 4: cand + 7 < p + 7 <= n - 5
+      }
+      N.v = v;
+      N.b4 = b4;
+      N.d = (valid && older) ? (uint32_t)(pc - cand) : 0u;
+
+      if (have_prev) finish(F);
+
+      __syncwarp();
+      if (valid) table[h] = (uint16_t)p;
+      __syncwarp();
+      for (;;) {
+        const bool lost = valid && table[h] < (uint16_t)p;
+        if (!__ballot_sync(FULL, lost)) break;
+        if (lost) table[h] = (uint16_t)p;
+        __syncwarp();
+      }
+    };
+
+    Pending2 PA, PB;
+    PA.c0 = PA.c1 = PA.v = PA.b4 = PA.d = 0;
+    PA.csh = 0;
+    PB = PA;
+    bool last_is_a = true;
+    for (int pos = 0; pos <= mflimit; pos += 64) {
+      step(pos, PA, PB, pos > 0);
+      last_is_a = true;
+      if (pos + 32 > mflimit) break;
+      step(pos + 32, PB, PA, true);
+      last_is_a = false;
+    }
+    if (last_is_a) finish(PA); else finish(PB);
+    __syncwarp();
+  }
+}
+
+// B2: thread per block around parse_block() of lz4_parse_core.h (host/device; unit-tested on the CPU against the oracle)
+struct ParseMemDev {
+  const uint4* __restrict__ ov;    // the block's off[] row, 8 positions per vector
+  const uint32_t* __restrict__ wp; // aligned word stream holding the block's bytes
+  int ovmax, kmax;
+  __device__ __forceinline__ uint4 off8(int i) const { return __ldcs(ov + (i < ovmax ? i : ovmax)); }
+  __device__ __forceinline__ uint32_t word(int k) const { return __ldg(wp + (k < kmax ? k : kmax)); }
+  __device__ __forceinline__ uint32_t cand_word(int k) const { return __ldg(wp + k); }
+};
+
+template <int CODEC>
+__global__ void __launch_bounds__(64) lz4_parse2_kernel(
+    const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
+    const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+    uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ offarr, uint2* __restrict__ seqarr,
+    uint32_t* __restrict__ nseq, uint32_t* __restrict__ csize, uint64_t* __restrict__ sizes) {
+  const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= m) return;
+  const uint32_t b = b0 + bl;
+  const BlockSpan B = block_span(src_base, src_off, src_len, blk_base, n_streams, b, block_size);
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(B.s);
+  const int sb = (int)(a0 & 3u);
+  ParseMemDev mem;
+  mem.ov = reinterpret_cast<const uint4*>(offarr + (size_t)bl * stride);
+  mem.wp = reinterpret_cast<const uint32_t*>(a0 & ~uintptr_t(3));
+  mem.ovmax = (int)(stride >> 3) - 1;
+  mem.kmax = B.n > 0 ? (sb + B.n - 1) >> 2 : 0;
+  const lzparse::Result r = lzparse::parse_block<CODEC>(mem, B.n, sb, stride, seqarr + (size_t)bl * max_seq);
+  nseq[b] = r.nseq;
+  if (CODEC != 2) {
+    csize[b] = r.csize;
+    sizes[b] = r.size;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // C: emission, one lane per sequence, into the block's final packed position; also writes the LZ4Block header
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lz4b_level(uint32_t block_size) {
@@ -475,6 +645,7 @@ __global__ void __launch_bounds__(kEmitThreads) lz4_emit_kernel(
   const uint32_t ns = nseq[b];
   const uint2* __restrict__ seq = seqarr + (size_t)bl * max_seq;
   const uint16_t* __restrict__ offp = offarr + (size_t)bl * stride;
+  const int omask = stride <= 32768u ? 0x7fff : 0xffff;
   for (uint32_t i0 = 0; i0 < ns; i0 += 32) {
     const uint32_t i = i0 + lane;
     bool slow = false;
@@ -486,7 +657,7 @@ __global__ void __launch_bounds__(kEmitThreads) lz4_emit_kernel(
       ml = (int)(r.y & 0xffffu);
       op = (int)(r.y >> 16);
       const int mlc = ml - kMinMatch;
-      if (ml) off = offp[anchor + lit];
+      if (ml) off = offp[anchor + lit] & omask;  // bit 15 of off[] is the parse kernel's "exactly 4" flag (blocks <= 32 KiB)
       if (lit <= 16 && ml && mlc < 15 + 510) {
         uint8_t* q = out + op;
         *q++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (mlc < 15 ? mlc : 15));
@@ -542,6 +713,7 @@ __global__ void __launch_bounds__(kEmitThreads) lz4_emit_kernel(
 // launchers
 // ------------------------------------------------------------------------------------------------------------
 int g_lz4_hlog = 12;  // B2S_LZ4_HLOG (api.cu reads it once at init); 12 is the specified default
+int g_lz4_pipe = 2;   // B2S_LZ4_PIPE: 2 = match2 + parse2 (off[] only, extension in the parse); 1 = first generation (A/B runs)
 
 template <int HLOG>
 static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
@@ -559,6 +731,23 @@ static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, c
   lz4_match_kernel<HLOG><<<(unsigned)grid, kMatchWarps * 32, smem, st>>>(
       src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, near_limit, d_off, d_ml,
       d_counter);
+}
+
+template <int HLOG>
+static void launch_match2_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                            const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
+                            uint32_t block_size, uint32_t stride, uint16_t* d_off, unsigned int* d_counter,
+                            cudaStream_t st) {
+  const size_t smem = (size_t)kMatchWarps * (2u << HLOG);
+  cudaFuncSetAttribute(lz4_match2_kernel<HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_match2_kernel<HLOG>, kMatchWarps * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  uint64_t want = ((uint64_t)m + kMatchWarps - 1) / kMatchWarps;
+  uint64_t grid = (uint64_t)kSMs * per_sm;  // persistent: one wave, warps pull blocks from the counter
+  if (grid > want) grid = want;
+  lz4_match2_kernel<HLOG><<<(unsigned)grid, kMatchWarps * 32, smem, st>>>(
+      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, d_off, d_counter);
 }
 
 size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size) {
@@ -583,6 +772,20 @@ static Lz4Ws carve_ws(uint8_t* d_ws, uint32_t m, uint32_t block_size) {
   return w;
 }
 
+template <int CODEC>
+static void launch_parse_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
+                           const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
+                           uint32_t block_size, const Lz4Ws& w, uint32_t* d_nseq, uint32_t* d_csize, uint64_t* d_sizes,
+                           cudaStream_t st) {
+  if (g_lz4_pipe == 1)
+    lz4_parse_kernel<CODEC><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
+                                                          w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+  else
+    lz4_parse2_kernel<CODEC><<<(m + 63) / 64, 64, 0, st>>>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m,
+                                                           block_size, w.stride, w.max_seq, w.off, w.seq, d_nseq,
+                                                           d_csize, d_sizes);
+}
+
 void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                       const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
                       uint32_t codec, uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches,
@@ -592,9 +795,12 @@ void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const 
   const Lz4Ws w = carve_ws(d_ws, m, block_size);
   cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), st);
   if (ev0) cudaEventRecord(ev0, st);
-#define B2S_LZ4M(H)                                                                                                  \
-  launch_match_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, near_limit, \
-                    w.off, w.ml, d_counter, st)
+#define B2S_LZ4M(H)                                                                                                    \
+  (g_lz4_pipe == 1                                                                                                     \
+       ? launch_match_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,         \
+                           near_limit, w.off, w.ml, d_counter, st)                                                     \
+       : launch_match2_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.off, \
+                            d_counter, st))
   switch (g_lz4_hlog) {
     case 10: B2S_LZ4M(10); break;
     case 11: B2S_LZ4M(11); break;
@@ -615,8 +821,7 @@ void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, c
   if (!m) return;
   const Lz4Ws w = carve_ws(d_ws, m, block_size);
   if (codec == B2S_CODEC_ZSTD) {
-    lz4_parse_kernel<2><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
-                                                      w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+    launch_parse_t<2>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w, d_nseq, d_csize, d_sizes, st);
     uint8_t* d_bits = d_ws + (size_t)m * w.stride * 4 + (size_t)m * w.max_seq * 8;
     // d_hash is unused by this codec and carries the bitstream sizes from the entropy stage to the emit kernel
     launch_zstd_seqenc(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq,
@@ -628,16 +833,14 @@ void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, c
     return;
   }
   if (codec == B2S_CODEC_SNAPPY_XERIAL) {
-    lz4_parse_kernel<1><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
-                                                         w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+    launch_parse_t<1>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w, d_nseq, d_csize, d_sizes, st);
     launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);
     launch_snappy_emit(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq,
                        w.off, w.seq, d_nseq, d_csize, d_sizes, dst_base, dst_cap, st, launches);
     *launches += 1;
     return;
   }
-  lz4_parse_kernel<0><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
-                                                    w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+  launch_parse_t<0>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w, d_nseq, d_csize, d_sizes, st);
   if (ev_parsed) cudaEventRecord(ev_parsed, st);  // B2S_TRACE timeline
   // packed offsets of this chunk's blocks, chained onto the running total of the chunks before it
   launch_exclusive_scan_u64(d_sizes + b0, m, d_running_total, d_scan_ws, st, launches, d_running_total);

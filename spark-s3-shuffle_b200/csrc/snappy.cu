@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kSnEmitThreads) snappy_emit_kernel(
       lit = (int)(r.x >> 16);
       ml = (int)(r.y & 0xffffu);
       op = (int)(r.y >> 16);
-      if (ml) off = offp[anchor + lit];
+      if (ml) off = offp[anchor + lit] & (stride <= 32768u ? 0x7fff : 0xffff);  // bit 15: parse flag (lz4_compress.cu)
       if (lit <= 16) {
         uint8_t* q = out + op;
         if (lit) {

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(64) zstd_seqenc_kernel(
           zstdenc::Seq q;
           q.ll = r.x >> 16;
           q.ml = r.y & 0xffffu;
-          q.off = offp[(r.x & 0xffffu) + q.ll];
+          q.off = offp[(r.x & 0xffffu) + q.ll] & (stride <= 32768u ? 0x7fffu : 0xffffu);  // bit 15: parse flag (lz4_compress.cu)
           return q;
         },
         bits + (size_t)bl * bits_stride, n);

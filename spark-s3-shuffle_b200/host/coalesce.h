@@ -45,7 +45,7 @@ struct CodecRequest {
 class CoalescingQueue {
  public:
   struct Statistics {
-    uint64_t calls = 0, batches = 0, maxMerged = 0, streams = 0;
+    uint64_t calls = 0, batches = 0, maxMerged = 0, streams = 0, isolated = 0;  // isolated: merged rounds re-run per request after a failure
   };
 
   // blocks until the request has been executed (by this thread or by another thread's round); returns its rc
@@ -115,16 +115,37 @@ class CoalescingQueue {
       rc = call(key, (uint32_t)total, src.data(), len.data(), dst.data(), cap.data(), dlen.data(), cks.data(),
                 slices ? nsl.data() : nullptr, slices ? sl.data() : nullptr, slices ? sc.data() : nullptr, status.data(),
                 bad.data());
-      if (rc != 0) err = b2s_last_error();
+      if (rc != 0) {
+        // A call-level failure of a MERGED batch (one task's truncated block, a header claiming an impossible size,
+        // ...) must not fail the tasks it happened to be merged with: the reference surfaces such errors per block,
+        // to the task that owns it.  Re-run the round one request at a time; only the offender keeps the error.
+        std::vector<int> rcs(round.size(), 0);
+        std::vector<std::string> errs(round.size());
+        for (size_t k = 0; k < round.size(); k++) {
+          CodecRequest* q = round[k];
+          rcs[k] = call(*q, q->n, q->src, q->src_len, q->dst, q->dst_cap, q->dst_len, q->checksum_out, q->n_slices,
+                        q->slice_len, q->slice_checksum, q->status, q->bad_slice);
+          if (rcs[k] != 0) errs[k] = b2s_last_error();
+        }
+        lk.lock();
+        stats_.batches += 1 + round.size();
+        stats_.isolated++;
+        stats_.maxMerged = std::max<uint64_t>(stats_.maxMerged, round.size());
+        for (size_t k = 0; k < round.size(); k++) {
+          round[k]->rc = rcs[k];
+          round[k]->error = errs[k];
+          round[k]->done = true;
+        }
+        cv_.notify_all();
+        return;
+      }
       at = 0;
       for (auto* q : round) {
         for (uint32_t i = 0; i < q->n; i++, at++) {
-          if (rc == 0) {
-            q->dst_len[i] = dlen[at];
-            q->status[i] = status[at];
-            if (q->checksum_out) q->checksum_out[i] = cks[at];
-            if (q->bad_slice) q->bad_slice[i] = bad[at];
-          }
+          q->dst_len[i] = dlen[at];
+          q->status[i] = status[at];
+          if (q->checksum_out) q->checksum_out[i] = cks[at];
+          if (q->bad_slice) q->bad_slice[i] = bad[at];
         }
       }
     }

@@ -24,7 +24,7 @@ using SourceFn = std::function<int64_t(uint8_t*, uint64_t)>;  // bytes read; <= 
 class B200CompressionCodec {
  public:
   B200CompressionCodec(int codecId, uint32_t blockSize, uint64_t flushBytes)
-      : codec_(codecId), blockSize_(blockSize), flushBytes_(flushBytes) {
+      : codec_(codecId), blockSize_(blockSize), flushBytes_(flushBytes < blockSize ? blockSize : flushBytes) {  // at least one codec block: 0 (an unparsable size) would spin write() forever
     if (codec_ == B2S_CODEC_NONE) throw UnsupportedOperationException("no compression codec configured");
   }
   int codecId() const { return codec_; }

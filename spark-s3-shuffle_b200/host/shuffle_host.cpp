@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <map>
 #include <memory>
@@ -169,10 +170,16 @@ class S3ShuffleDispatcher {
   }
   // :174-188 removeShuffle: every prefix folder
   void removeShuffle(int32_t shuffleId) const {
+    // fs.delete(path, true) in the reference — no shell involved.  rootDir / app id come from user configuration: an
+    // empty, relative or "/" root would aim a recursive delete at the working directory or the file system root.
+    namespace fs = std::filesystem;
+    const std::string root = localRoot();
+    if (root.empty() || root[0] != '/' || fs::path(root).lexically_normal() == fs::path("/") || appId.empty() ||
+        appId.find('/') != std::string::npos)
+      return;
     for (int i = 0; i < folderPrefixes; i++) {
-      std::string dir = shuffleDir(i, shuffleId);
-      std::string cmd = "rm -rf '" + dir + "'";
-      if (system(cmd.c_str()) != 0) { /* like the reference: failures are only logged */ }
+      std::error_code ec;
+      fs::remove_all(fs::path(shuffleDir(i, shuffleId)), ec);  // like the reference: failures are only logged
     }
   }
   int codecId() const {
@@ -559,6 +566,8 @@ static std::deque<S3BufferedPrefetchIterator::Source> computeShuffleBlockStreams
       ShuffleBlockInfo bi;
       bi.id = (re - rs > 1) ? BlockId{BlockId::ShuffleBatch, shuffleId, mapId, rs, re}
                             : BlockId{BlockId::Shuffle, shuffleId, mapId, rs, re};
+      if (verify && sums.size() < (size_t)re)  // a short or stale .checksum object (the reference: ArrayIndexOutOfBounds)
+        throw SparkException("Checksum file of " + bi.id.name() + " holds fewer entries than the index");
       if (verify)
         for (int32_t r = rs; r < re; r++) {    // S3ChecksumValidationStream walks the .index differences (:68-86)
           bi.sliceLen.push_back((uint64_t)(acc[(size_t)r + 1] - acc[(size_t)r]));

@@ -41,8 +41,10 @@ def test_concurrent_callers_are_merged_and_get_their_own_results(harness):
     assert st["backend_calls"] == st["batches"] < st["calls"] and 2 <= st["maxMerged"] <= 8
 
 
-def test_a_call_level_failure_reaches_exactly_the_merged_callers(harness):
+def test_a_call_level_failure_of_a_merged_batch_is_isolated_per_request(harness):
+    """one failing backend call: a merged round is re-run request by request (the stand-in fails only once, so every
+    task then succeeds); only a request that failed on its own keeps the error — nobody pays for a neighbour's block"""
     bad, st = run(harness, 6, 10, fail_one=1)
     assert bad == 0
-    assert 1 <= st["failed"] <= 6            # the requests that were in the failing batch, nobody else
+    assert st["failed"] <= 1
     assert st["calls"] == 6 * 10 * 2 - st["failed"]   # a failed compress skips its read-back

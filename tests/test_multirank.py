@@ -35,7 +35,7 @@ def test_round_robin_sharding_and_metadata_gather_world2():
 
 def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     r = _torchrun([os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
-                   "--blocks", "40", "--cpu-sample-blocks", "40"])
+                   "--blocks", "40", "--cpu-sample-bytes", "30000000"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -54,7 +54,7 @@ def test_reference_arm_contract_for_every_codec(codec):
     import subprocess
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--codec", codec, "--steps", "1",
-                        "--warmup", "1", "--blocks", "30", "--cpu-sample-blocks", "30"], capture_output=True, text=True,
+                        "--warmup", "1", "--blocks", "30", "--cpu-sample-bytes", "20000000"], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]

@@ -1,0 +1,138 @@
+"""CPU check of spark-s3-shuffle_b200/csrc/lz4_parse_core.h — the per-thread body of lz4_parse2_kernel — against the
+oracle's executable specification (orc_lz4_compress_block_win, orc_snappy_compress_raw_win via xerial framing).
+
+The header is compiled by g++ into tests/native/lz4_parse_host.cpp together with a plain restatement of what the match
+kernel hands it (off[] + the "exactly 4" flag); the records are turned into LZ4 block bytes here and must equal the
+oracle's bytes.  No GPU involved; the GPU suite then demands the same bytes from the kernels themselves.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "native", "lz4_parse_host.cpp")
+HDR = os.path.join(ROOT, "spark-s3-shuffle_b200", "csrc", "lz4_parse_core.h")
+
+
+@pytest.fixture(scope="module")
+def ph(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("parse_core") / "libparse_host.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Werror", "-o", so, SRC])
+    L = C.CDLL(so)
+    L.ph_parse.restype = C.c_int
+    L.ph_parse.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def parse(L, codec, data, sb=0, hash_log=12):
+    a = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(0, dtype=np.uint8)
+    n = a.size
+    rec = np.zeros(3 * (n // 4 + 2) + 8, dtype=np.uint32)
+    nseq, csize, size = C.c_uint32(), C.c_uint32(), C.c_uint64()
+    buf = np.ascontiguousarray(a)
+    rc = L.ph_parse(codec, buf.ctypes.data if n else None, n, sb, hash_log, C.byref(nseq), C.byref(csize), C.byref(size),
+                    rec.ctypes.data)
+    assert rc == 0
+    k = nseq.value
+    recs = rec[: 2 * k].reshape(k, 2)
+    offs = rec[2 * (n // 4 + 2): 2 * (n // 4 + 2) + k]
+    return recs, offs, csize.value, size.value
+
+
+def lz4_bytes_from_records(data, recs, offs):
+    """lz4_emit_kernel's layout: token, literal length bytes, literals, LE16 offset, match length bytes"""
+    out = bytearray()
+    for (x, y), off in zip(recs.tolist(), offs.tolist()):
+        anchor, lit, ml, op = x & 0xFFFF, x >> 16, y & 0xFFFF, y >> 16
+        assert op == len(out), "record's output offset is not the running sum"
+        mlc = ml - 4
+        out.append((min(lit, 15) << 4) | (min(mlc, 15) if ml else 0))
+        if lit >= 15:
+            r = lit - 15
+            while r >= 255:
+                out.append(255)
+                r -= 255
+            out.append(r)
+        out += data[anchor:anchor + lit]
+        if ml:
+            out += bytes([off & 0xFF, off >> 8])
+            if mlc >= 15:
+                r = mlc - 15
+                while r >= 255:
+                    out.append(255)
+                    r -= 255
+                out.append(r)
+    return bytes(out)
+
+
+def corpora():
+    rng = np.random.default_rng(7)
+    tera = oracle.gen_terasort(3, 700).tobytes()
+    words = [b"shuffle", b"block", b"spark", b"partition", b"index", b"checksum", b" ", b"\n", b"s3a://bucket/", b"0000"]
+    text = b"".join(words[i] for i in rng.integers(0, len(words), 9000))
+    rows = b"".join(int(v).to_bytes(8, "little") + b"\x00" * 8 + int(v % 97).to_bytes(8, "little")
+                    for v in rng.zipf(1.3, 1500))
+    return {
+        "terasort": tera, "zeros": bytes(40000), "random": rng.integers(0, 256, 33000, dtype=np.uint8).tobytes(),
+        "text": text, "rows": rows, "period3": (b"abc" * 12000), "period7": (b"0123456" * 5000),
+        "runs": b"".join(bytes([i & 255]) * (1 + (i * 7) % 40) for i in range(2500)),
+        "ab_long": b"A" * 300 + rng.integers(0, 256, 100, dtype=np.uint8).tobytes() + b"A" * 5000 + b"tail-bytes-here",
+    }
+
+
+@pytest.mark.parametrize("name", sorted(corpora().keys()))
+def test_lz4_records_equal_the_specification(ph, name):
+    data = corpora()[name]
+    for n in (32768, 32767, 20001, 4097, 64, 40, 13, 12, 5, 1, 0):
+        blk = data[:n]
+        if len(blk) < n:
+            continue
+        want = oracle.lz4_compress_block(blk, win=True, cap=max(len(blk) - 1, 0)) if n else None
+        for sb in range(4):
+            recs, offs, csize, size = parse(ph, 0, blk, sb)
+            if want is None:  # does not fit below originalLength: LZ4BlockOutputStream stores RAW
+                assert csize == (n | 0x80000000) and size == 21 + n, (name, n, sb)
+                continue
+            got = lz4_bytes_from_records(blk, recs, offs)
+            assert got == want, (name, n, sb)
+            assert csize == len(want) and size == 21 + len(want)
+
+
+def test_lz4_64k_blocks_without_the_flag(ph):
+    """rows longer than 32768 positions cannot spare bit 15: every match goes through the extension"""
+    c = corpora()
+    data = (c["terasort"] + c["text"] + c["zeros"])[:65536]
+    for n in (65536, 50000, 32800):
+        blk = data[:n]
+        want = oracle.lz4_compress_block(blk, win=True, cap=n - 1)
+        recs, offs, csize, _ = parse(ph, 0, blk, 1)
+        assert want is not None and lz4_bytes_from_records(blk, recs, offs) == want and csize == len(want)
+
+
+def test_snappy_and_zstd_variants_agree_on_the_sequences(ph):
+    c = corpora()
+    for name in ("terasort", "text", "zeros", "runs", "random"):
+        blk = c[name][:32768]
+        r0, o0, _, _ = parse(ph, 0, blk, 2)
+        r1, o1, cs1, sz1 = parse(ph, 1, blk, 2)
+        r2, o2, _, _ = parse(ph, 2, blk, 2)
+        # the Snappy element stream of the specification has exactly csize bytes (xerial: BE32 length + block)
+        x = oracle.xerial_compress(blk, 32768, compressor=1)
+        assert len(x) == 16 + 4 + cs1 and sz1 == 4 + cs1, name
+        # same matches in all three grammars (LZ4 may stop early only when it falls back to RAW, which these do not)
+        m0 = [(int(x_ & 0xFFFF) + int(x_ >> 16), int(y & 0xFFFF), int(o)) for (x_, y), o in zip(r0.tolist(), o0.tolist()) if y & 0xFFFF]
+        m1 = [(int(x_ & 0xFFFF) + int(x_ >> 16), int(y & 0xFFFF), int(o)) for (x_, y), o in zip(r1.tolist(), o1.tolist()) if y & 0xFFFF]
+        m2 = [(int(x_ & 0xFFFF) + int(x_ >> 16), int(y & 0xFFFF), int(o)) for (x_, y), o in zip(r2.tolist(), o2.tolist()) if y & 0xFFFF]
+        if name != "random":
+            assert m0 == m1 == m2, name
+        # Zstandard records carry the running literal count and end with the trailing-literals record
+        lits = 0
+        for x_, y in r2.tolist():
+            assert (y >> 16) == lits
+            lits += x_ >> 16
+        assert lits + sum(m[1] for m in m2) == len(blk)
