@@ -72,6 +72,41 @@ def usable_cores():
     return cores, n, quota
 
 
+def bind_process_to_gpu_node(gpu_index):
+    """sched_setaffinity + set_mempolicy(MPOL_PREFERRED) to the NUMA node of GPU `gpu_index` (sysfs; no libnuma).
+    Returns the node or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                           text=True, timeout=30).stdout
+        bdf = None
+        for line in q.strip().splitlines():
+            idx, b = [x.strip() for x in line.split(",")]
+            if int(idx) == gpu_index:
+                bdf = b.lower()
+        if bdf is None:
+            return None
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        libc.syscall(238, 1, mask, 1025)  # SYS_set_mempolicy, MPOL_PREFERRED
+        return node
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -248,6 +283,11 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ B200 arm
+    # NUMA first, before torch / CUDA / NCCL create their helper threads and arenas: the whole rank process (its threads,
+    # page cache, pinned staging) lives on the socket its GPU hangs off.  GPUs 0-3 / 4-7 sit on different sockets of the
+    # 8-GPU hosts; round 1's ranks floated over both and the host-staged path lost half its scaling to cross-socket
+    # traffic.  The C ABI repeats the placement for its own allocations (b2s_bind_thread_to_device).
+    early_numa = bind_process_to_gpu_node(local_rank) if os.environ.get("B2S_NUMA", "1") != "0" else None
     import torch
 
     torch.cuda.set_device(local_rank)
@@ -457,7 +497,7 @@ def main():
                    "h2d_bytes_per_step": int((tw2["h2d_bytes"] + tr2["h2d_bytes"]) * waves),
                    "d2h_bytes_per_step": int((tw2["d2h_bytes"] + tr2["d2h_bytes"]) * waves),
                    "ms_per_step": round(c_elapsed / args.e2e_steps * 1e3, 2), "steps": args.e2e_steps,
-                   "blocks_per_gpu": n * waves, "numa_node": numa_node,
+                   "blocks_per_gpu": n * waves, "numa_node": numa_node, "process_bound_to_node": early_numa,
                    "write_ms": round(tw2["total_ms"], 2), "read_ms": round(tr2["total_ms"], 2),
                    "write_sums_ms": {k: round(tw2[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
                    "read_sums_ms": {k: round(tr2[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},

@@ -252,7 +252,17 @@ static void win_find_offsets(const uint8_t* src, int n, int hash_log, uint16_t* 
   free(table);
 }
 
-int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap, int hash_log) {
+/* Sub-chunk size the GPU parse uses for codec blocks of `block_size` bytes: 1/32 of the (32-rounded) block, itself
+ * rounded up to a multiple of 32 — one sub-chunk per lane of the warp that parses the block (lz4_parse4_kernel). */
+int orc_lz4_subchunk(uint32_t block_size) {
+  const uint32_t stride = (block_size + 31u) & ~31u;
+  return (int)(((stride >> 5) + 31u) & ~31u);
+}
+
+/* sub > 0: the greedy parse restarts at every multiple of `sub` — a match neither starts in the last three positions of
+ * a sub-chunk nor extends past its end (the 32 lanes of a warp parse the 32 sub-chunks of a block independently).
+ * sub == 0: one parse over the whole block (the round-1 kernels, still used for Snappy and Zstandard). */
+int orc_lz4_compress_block_win_sub(const uint8_t* src, int n, uint8_t* dst, int cap, int hash_log, int sub) {
   if (n > 65536 || hash_log > 16 || hash_log < 4) return 0;
   uint16_t* off = (uint16_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(uint16_t));
   int op = 0, anchor = 0;
@@ -262,13 +272,24 @@ int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap,
     win_find_offsets(src, n, hash_log, off); /* phase A */
     int p = 0;                                /* phase B + C */
     while (p <= mflimit) {
+      int chunk_hi = n;
+      if (sub > 0) {
+        chunk_hi = (p / sub + 1) * sub;
+        if (chunk_hi > n) chunk_hi = n;
+      }
+      const int plim = mflimit < chunk_hi - 4 ? mflimit : chunk_hi - 4;
+      const int elim = matchlimit < chunk_hi ? matchlimit : chunk_hi;
+      if (p > plim) { /* nothing can start in the rest of this sub-chunk */
+        p = chunk_hi;
+        continue;
+      }
       if (!off[p]) {
         p++;
         continue;
       }
       const int c = p - off[p];
       int mlen = LZ4_MINMATCH;
-      while (p + mlen < matchlimit && src[p + mlen] == src[c + mlen]) mlen++;
+      while (p + mlen < elim && src[p + mlen] == src[c + mlen]) mlen++;
       op = lz4_emit_seq(src, anchor, p - anchor, off[p], mlen, dst, op, cap);
       if (op < 0) {
         free(off);
@@ -281,6 +302,9 @@ int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap,
   op = lz4_emit_seq(src, anchor, n - anchor, 0, 0, dst, op, cap);
   free(off);
   return op < 0 ? 0 : op;
+}
+int orc_lz4_compress_block_win(const uint8_t* src, int n, uint8_t* dst, int cap, int hash_log) {
+  return orc_lz4_compress_block_win_sub(src, n, dst, cap, hash_log, 0);
 }
 
 /* LZ4_decompress_fast semantics (lz4 1.9.4 LZ4_decompress_unsafe_generic), plus input bounds checks */
@@ -380,7 +404,7 @@ static int64_t lz4block_compress_impl(const uint8_t* src, uint64_t n, uint32_t b
     if (ext)
       clen = ext((const char*)(src + off), (char*)tmp, (int)o, tcap);
     else if (compressor == 1)
-      clen = (o <= 65536) ? orc_lz4_compress_block_win(src + off, (int)o, tmp, (int)o - 1, 12) : 0;
+      clen = (o <= 65536) ? orc_lz4_compress_block_win_sub(src + off, (int)o, tmp, (int)o - 1, 12, orc_lz4_subchunk(block_size)) : 0;
     else
       clen = orc_lz4_compress_block(src + off, (int)o, tmp, tcap);
     int method = LZ4B_LZ4;

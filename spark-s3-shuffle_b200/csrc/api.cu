@@ -359,8 +359,18 @@ struct CompressDevMeta {
   unsigned int* counter;
 };
 
+// Compression level.  LZ4Block and Snappy have none in the reference either (lz4-java's fast compressor, snappy-java);
+// for Zstandard (spark.io.compression.zstd.level, codec chosen at storage/S3ShuffleReader.scala:57-60) the level sets the
+// match finder's hash-table size: 1 -> 2^11 entries per block (fastest), 2 / unspecified -> 2^12, >= 3 -> 2^13 (more
+// shared memory per warp, fewer resident warps, more matches found).
+int hlog_for_level(uint32_t codec, int32_t level) {
+  if (codec != B2S_CODEC_ZSTD || level <= 0) return 0;
+  return level == 1 ? 11 : level == 2 ? 12 : 13;
+}
+
 int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t bs, uint32_t alg, CompressJob& J,
-                     const uint8_t* d_src, uint8_t* d_dst, uint64_t dst_cap, CompressDevMeta& M, uint64_t* launches) {
+                     const uint8_t* d_src, uint8_t* d_dst, uint64_t dst_cap, CompressDevMeta& M, uint64_t* launches,
+                     int32_t level) {
   const uint32_t n = J.n, nb = J.nb;
   const uint32_t chunk = std::min<uint32_t>(nb ? nb : 1, g_lz4_chunk_blocks);
   size_t ws_elems = std::max(scan_ws_elems(nb + 1), checksum_ws_elems(n)) + 4;
@@ -368,7 +378,7 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
                 align_up(((size_t)n + 1) * 8, 16) + ws_elems * 8 + 256;
   int rc = S.meta.ensure(need);
   if (rc) return rc;
-  const size_t ws_bytes = align_up(lz4_compress_ws_bytes(chunk, bs), 256);
+  const size_t ws_bytes = align_up(lz4_compress_ws_bytes(chunk, bs, J.codec), 256);
   rc = S.scratch.ensure(ws_bytes * (nb > chunk ? 2 : 1));
   if (rc) return rc;
   Carver dc(S.meta.p);
@@ -422,7 +432,7 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
     S.dom_pair(&e0, &e1);
     if (k >= 2) CU(cudaStreamWaitEvent(S.st2, S.ev_free[par], 0));  // emit of chunk k-2 has released this workspace
     launch_lz4_match(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, codec, ws, M.counter + par, S.st2, launches,
-                     e0, e1);
+                     e0, e1, hlog_for_level(codec, level));
     CU(cudaEventRecord(S.ev_match[par], S.st2));
     CU(cudaStreamWaitEvent(st, S.ev_match[par], 0));
     cudaEvent_t t0 = nullptr, t1 = nullptr, tp = nullptr;
@@ -859,6 +869,9 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
   g_lz4_hlog = env_int("B2S_LZ4_HLOG", g_lz4_hlog);
   g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
   g_lz4_pipe = env_int("B2S_LZ4_PIPE", g_lz4_pipe);
+  g_lz4d_tokens = env_int("B2S_LZ4D_TOKENS", g_lz4d_tokens);
+  g_lz4_match_depth = env_int("B2S_LZ4_MATCH_DEPTH", g_lz4_match_depth);
+  g_lz4d_copy_group = env_int("B2S_LZ4D_COPYGROUP", g_lz4d_copy_group);
   g_lz4_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4_CHUNK_BLOCKS", (int)g_lz4_chunk_blocks));
   g_lz4d_legacy = env_int("B2S_LZ4D_LEGACY", 0);
   g_trace = env_int("B2S_TRACE", 0);
@@ -1209,7 +1222,6 @@ int b2s_compress_dev(uint32_t dev_index, uint32_t codec, int32_t level, uint32_t
                      uint32_t checksum_alg, uint32_t n, const void* d_src_base, const uint64_t* src_off,
                      const uint64_t* src_len, void* d_dst_base, uint64_t dst_cap, uint64_t* dst_off,
                      uint64_t* dst_len, uint64_t* dst_total, uint64_t* checksum_out, int32_t* status) {
-  (void)level;
   WallTimer wt;
   t_timing = b2s_timing{};
   Device* D;
@@ -1231,7 +1243,7 @@ int b2s_compress_dev(uint32_t dev_index, uint32_t codec, int32_t level, uint32_t
   CompressDevMeta M;
   uint64_t launches = 0;
   rc = compress_enqueue(g_ctx, S, D->tabs, bs, checksum_alg, J, (const uint8_t*)d_src_base, (uint8_t*)d_dst_base,
-                        dst_cap, M, &launches);
+                        dst_cap, M, &launches, level);
   if (rc) return rc;
   CU(cudaEventSynchronize(S.ev_a));
   CU(cudaGetLastError());
@@ -1255,7 +1267,7 @@ int b2s_compress_dev(uint32_t dev_index, uint32_t codec, int32_t level, uint32_t
 }
 
 // shared engine for the host-pointer write path.  packed_dst != nullptr: outputs back to back into that arena.
-static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg, uint32_t n,
+static int compress_host(uint32_t codec, int32_t level, uint32_t codec_block_size, uint32_t alg, uint32_t n,
                          const uint8_t* const* src, const uint64_t* src_len, uint8_t* packed_dst, uint64_t packed_cap,
                          uint8_t* const* dst, const uint64_t* dst_cap, uint64_t* dst_off, uint64_t* dst_len,
                          uint64_t* dst_total, uint64_t* checksum_out, int32_t* status) {
@@ -1352,7 +1364,7 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
     t_timing.src_bytes += bytes;
     CompressDevMeta M;
     rc = compress_enqueue(g_ctx, S, D->tabs, bs, alg, J, (const uint8_t*)S.src.p, (uint8_t*)S.dst.p, S.dst.cap, M,
-                          &launches);
+                          &launches, level);
     if (rc) return rc;
   }
   for (size_t c = nchunks > (size_t)g_nslot ? nchunks - g_nslot : 0; c < nchunks; c++) {
@@ -1374,11 +1386,10 @@ static int compress_host(uint32_t codec, uint32_t codec_block_size, uint32_t alg
 int b2s_compress_batch(uint32_t codec, int32_t level, uint32_t codec_block_size, uint32_t checksum_alg, uint32_t n,
                        const uint8_t* const* src, const uint64_t* src_len, uint8_t* const* dst,
                        const uint64_t* dst_cap, uint64_t* dst_len, uint64_t* checksum_out, int32_t* status) {
-  (void)level;
   if (n && (!src || !src_len || !dst || !dst_cap || !dst_len || !status)) return fail(B2S_E_ARG, "null argument%s");
   if (!want_sharding(n)) {
     std::vector<uint64_t> off(n);
-    return compress_host(codec, codec_block_size, checksum_alg, n, src, src_len, nullptr, 0, dst, dst_cap, off.data(),
+    return compress_host(codec, level, codec_block_size, checksum_alg, n, src, src_len, nullptr, 0, dst, dst_cap, off.data(),
                          dst_len, nullptr, checksum_out, status);
   }
   return shard_over_devices(n, [&](const std::vector<uint32_t>& idx) {
@@ -1393,7 +1404,7 @@ int b2s_compress_batch(uint32_t codec, int32_t level, uint32_t codec_block_size,
       dp[k] = dst[idx[k]];
       dc[k] = dst_cap[idx[k]];
     }
-    int rc = compress_host(codec, codec_block_size, checksum_alg, m, sp.data(), sl.data(), nullptr, 0, dp.data(),
+    int rc = compress_host(codec, level, codec_block_size, checksum_alg, m, sp.data(), sl.data(), nullptr, 0, dp.data(),
                            dc.data(), off.data(), dl.data(), nullptr, ck.data(), st.data());
     if (!rc)
       for (uint32_t k = 0; k < m; k++) {
@@ -1409,12 +1420,11 @@ int b2s_compress_packed(uint32_t codec, int32_t level, uint32_t codec_block_size
                         const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
                         uint64_t dst_cap, uint64_t* dst_off, uint64_t* dst_len, uint64_t* dst_total,
                         uint64_t* checksum_out, int32_t* status) {
-  (void)level;
   if (n && (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_len || !status))
     return fail(B2S_E_ARG, "null argument%s");
   std::vector<const uint8_t*> ptr(n);
   for (uint32_t i = 0; i < n; i++) ptr[i] = src_base + src_off[i];
-  return compress_host(codec, codec_block_size, checksum_alg, n, ptr.data(), src_len, dst_base, dst_cap, nullptr,
+  return compress_host(codec, level, codec_block_size, checksum_alg, n, ptr.data(), src_len, dst_base, dst_cap, nullptr,
                        nullptr, dst_off, dst_len, dst_total, checksum_out, status);
 }
 

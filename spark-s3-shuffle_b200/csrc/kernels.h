@@ -42,9 +42,9 @@ void launch_xxh32_verify(const BlockDesc* d_desc, uint32_t n_blocks, const uint8
                          uint32_t mask, int32_t* d_status, cudaStream_t st, uint64_t* launches);
 
 // ---------------- lz4_compress.cu (K3: match / parse / emit + write-side LZ4Block framing) ----------------
-extern int g_lz4_hlog, g_lz4d_tile, g_lz4_pipe;
+extern int g_lz4_hlog, g_lz4d_tile, g_lz4_pipe, g_lz4d_tokens, g_lz4_match_depth, g_lz4d_copy_group;
 // bytes of workspace for one pass over `chunk_blocks` codec blocks (off u16 + ml8 u8 per position, 8-byte records)
-size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size);
+size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size, uint32_t codec);
 // Codec blocks [b0, b0+m) of the batch, in two halves that may run on different streams (d_ws is handed from one to
 // the other):  launch_lz4_match = phase A (per-position off/ml into d_ws; ev0/ev1 bracket the kernel);
 // launch_lz4_parse_emit = parse -> scan(d_sizes[b0..b0+m), chained on *d_running_total) -> emit (+ 21-byte headers)
@@ -54,7 +54,7 @@ size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size);
 void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                       const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
                       uint32_t codec, uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches,
-                      cudaEvent_t ev0, cudaEvent_t ev1);
+                      cudaEvent_t ev0, cudaEvent_t ev1, int hlog = 0 /* 0 = B2S_LZ4_HLOG (12) */);
 void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                            const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
                            uint32_t block_size, uint32_t codec, uint8_t* d_ws, uint32_t* d_nseq, uint32_t* d_csize,

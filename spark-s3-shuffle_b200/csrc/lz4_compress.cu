@@ -430,11 +430,12 @@ struct Pending2 {
   unsigned csh;
 };
 
-template <int HLOG>
+template <int HLOG, int DEPTH>
 __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
     const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
     const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
-    uint32_t stride, uint16_t* __restrict__ offarr, unsigned int* __restrict__ work_counter) {
+    uint32_t stride, uint16_t* __restrict__ offarr, uint32_t* __restrict__ maskarr,
+    unsigned int* __restrict__ work_counter) {
   extern __shared__ __align__(16) uint16_t smem_tables[];
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
     const uint8_t* __restrict__ s = B.s;
     const int n = B.n;
     uint16_t* oq = offarr + (size_t)bl * stride + r_me;
+    uint32_t* mq = maskarr + (size_t)bl * (stride >> 5);  // one word per window: bit r = position r matched
     {
       uint4* t4 = reinterpret_cast<uint4*>(table);
       for (int j = lane; j < (1 << HLOG) / 8; j += 32) t4[j] = make_uint4(0, 0, 0, 0);
@@ -466,6 +468,9 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
       if (flag4 && off && (((W.c1 >> W.csh) ^ W.b4) & 0xffu)) off |= 0x8000u;
       __stcs(oq, (uint16_t)off);
       oq += 32;
+      const unsigned mb = __ballot_sync(FULL, off != 0u);
+      if (lane == 0) *mq = __brev(mb);
+      mq++;
     };
 
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(s + (r_me <= mflimit ? r_me : mflimit));
@@ -524,10 +529,39 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
       }
     };
 
-    Pending2 PA, PB;
+    Pending2 PA, PB, PC;
     PA.c0 = PA.c1 = PA.v = PA.b4 = PA.d = 0;
     PA.csh = 0;
     PB = PA;
+    PC = PA;
+    if (DEPTH == 2) {
+      // candidate words requested TWO windows ahead of their use (three pending windows rotate): ncu of the one-ahead
+      // loop shows the kernel waiting on them (long_scoreboard 6 warps per issue, issue slots 54 % busy)
+      int k = 0;
+      for (int pos = 0; pos <= mflimit; pos += 96) {
+        step(pos, PA, PB, pos > 0);  // finishes the window requested two steps ago
+        k = 1;
+        if (pos + 32 > mflimit) break;
+        step(pos + 32, PB, PC, pos > 0);
+        k = 2;
+        if (pos + 64 > mflimit) break;
+        step(pos + 64, PC, PA, true);
+        k = 3;
+      }
+      // two windows are still pending, oldest first
+      if (k == 1) {
+        if (mflimit >= 32) finish(PC);
+        finish(PA);
+      } else if (k == 2) {
+        finish(PA);
+        finish(PB);
+      } else {
+        finish(PB);
+        finish(PC);
+      }
+      __syncwarp();
+      continue;
+    }
     bool last_is_a = true;
     for (int pos = 0; pos <= mflimit; pos += 64) {
       step(pos, PA, PB, pos > 0);
@@ -545,18 +579,22 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
 struct ParseMemDev {
   const uint4* __restrict__ ov;    // the block's off[] row, 8 positions per vector
   const uint32_t* __restrict__ wp; // aligned word stream holding the block's bytes
+  const uint32_t* __restrict__ mk; // the block's window masks (event-driven variant)
   int ovmax, kmax;
+  __device__ __forceinline__ uint32_t mask(int w) const { return __ldg(mk + w); }
+  __device__ __forceinline__ uint32_t off16(int q) const { return __ldg(reinterpret_cast<const uint16_t*>(ov) + q); }
   __device__ __forceinline__ uint4 off8(int i) const { return __ldcs(ov + (i < ovmax ? i : ovmax)); }
   __device__ __forceinline__ uint32_t word(int k) const { return __ldg(wp + (k < kmax ? k : kmax)); }
   __device__ __forceinline__ uint32_t cand_word(int k) const { return __ldg(wp + k); }
 };
 
-template <int CODEC>
+template <int CODEC, bool EV>
 __global__ void __launch_bounds__(64) lz4_parse2_kernel(
     const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
     const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
-    uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ offarr, uint2* __restrict__ seqarr,
-    uint32_t* __restrict__ nseq, uint32_t* __restrict__ csize, uint64_t* __restrict__ sizes) {
+    uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ offarr, const uint32_t* __restrict__ maskarr,
+    uint2* __restrict__ seqarr, uint32_t* __restrict__ nseq, uint32_t* __restrict__ csize,
+    uint64_t* __restrict__ sizes) {
   const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= m) return;
   const uint32_t b = b0 + bl;
@@ -566,13 +604,142 @@ __global__ void __launch_bounds__(64) lz4_parse2_kernel(
   ParseMemDev mem;
   mem.ov = reinterpret_cast<const uint4*>(offarr + (size_t)bl * stride);
   mem.wp = reinterpret_cast<const uint32_t*>(a0 & ~uintptr_t(3));
+  mem.mk = maskarr + (size_t)bl * (stride >> 5);
   mem.ovmax = (int)(stride >> 3) - 1;
   mem.kmax = B.n > 0 ? (sb + B.n - 1) >> 2 : 0;
-  const lzparse::Result r = lzparse::parse_block<CODEC>(mem, B.n, sb, stride, seqarr + (size_t)bl * max_seq);
+  const lzparse::Result r = EV ? lzparse::parse_block_ev<CODEC>(mem, B.n, sb, stride, seqarr + (size_t)bl * max_seq)
+                               : lzparse::parse_block<CODEC>(mem, B.n, sb, stride, seqarr + (size_t)bl * max_seq);
   nseq[b] = r.nseq;
   if (CODEC != 2) {
     csize[b] = r.csize;
     sizes[b] = r.size;
+  }
+}
+
+// B4: sub-chunk parallel parse — one WARP per codec block, lane k parses sub-chunk k (lz4_parse_core.h, walk_subchunk),
+// then the warp stitches the 32 staged record lists into the dense record array the emit kernels read:
+//   1. anchors: the first sequence of a sub-chunk owns the literals since the last match of any earlier sub-chunk
+//      (inclusive max-scan of the lanes' last match ends);
+//   2. sizes: size of that first sequence + the lane's remaining sequences -> exclusive scan = the lane's output offset
+//      inside the block (Zstandard: literal bytes instead of output bytes);
+//   3. compaction in place: lane k staged its records at slot k * (S/4 + 1); dense index <= staged index, so batches of
+//      32 records are read, patched (anchor / literal count of a first record, offsets made absolute) and written back
+//      in increasing order without ever overwriting an unread record;
+//   4. the block's final literal run, its record count and sizes (RAW decision for LZ4Block).
+constexpr int kParse4Warps = 4;
+__host__ __device__ inline uint32_t parse4_sub(uint32_t stride) { return ((stride >> 5) + 31u) & ~31u; }
+
+template <int CODEC>
+__global__ void __launch_bounds__(kParse4Warps * 32) lz4_parse4_kernel(
+    const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
+    const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
+    uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ offarr, const uint32_t* __restrict__ maskarr,
+    uint2* seqarr, uint32_t* __restrict__ nseq, uint32_t* __restrict__ csize, uint64_t* __restrict__ sizes) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr bool SNAPPY = CODEC == 1, ZSTD = CODEC == 2;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bl = blockIdx.x * kParse4Warps + (threadIdx.x >> 5);
+  if (bl >= m) return;  // warp-uniform
+  const uint32_t b = b0 + bl;
+  const BlockSpan B = block_span(src_base, src_off, src_len, blk_base, n_streams, b, block_size);
+  const int n = B.n;
+  const int S = (int)parse4_sub(stride);
+  const int slot = S / 4 + 1;
+  uint2* seq = seqarr + (size_t)bl * max_seq;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(B.s);
+  const int sb = (int)(a0 & 3u);
+  ParseMemDev mem;
+  mem.ov = reinterpret_cast<const uint4*>(offarr + (size_t)bl * stride);
+  mem.wp = reinterpret_cast<const uint32_t*>(a0 & ~uintptr_t(3));
+  mem.mk = maskarr + (size_t)bl * (stride >> 5);
+  mem.ovmax = (int)(stride >> 3) - 1;
+  mem.kmax = n > 0 ? (sb + n - 1) >> 2 : 0;
+
+  const int lo = lane * S;
+  lzparse::SubResult R;
+  R.nrec = 0;
+  R.rest = 0;
+  R.pm0 = R.len0 = R.d0 = 0;
+  R.last_end = -1;
+  if (n >= kMFLimit + 1 && lo < n) {
+    const int hi = lo + S < n ? lo + S : n;
+    R = lzparse::walk_subchunk<CODEC>(mem, n, sb, stride, lo, hi, seq + (size_t)lane * slot);
+  }
+  __syncwarp();  // staged records are visible to the other lanes
+
+  // 1. anchor of my first sequence = the last match end of any earlier lane (0 if none)
+  int amax = R.last_end;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, amax, d);
+    if (lane >= d && t > amax) amax = t;
+  }
+  int anchor_in = __shfl_up_sync(FULL, amax, 1);
+  if (lane == 0 || anchor_in < 0) anchor_in = 0;
+  const int anchor_f = __shfl_sync(FULL, amax, 31) < 0 ? 0 : __shfl_sync(FULL, amax, 31);
+  // 2. sizes and counts
+  const int size0 = R.nrec ? lzparse::seq_size<CODEC>(R.pm0 - anchor_in, R.len0, R.d0) : 0;
+  int inc = size0 + R.rest, cnt = R.nrec;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, inc, d), u = __shfl_up_sync(FULL, cnt, d);
+    if (lane >= d) {
+      inc += t;
+      cnt += u;
+    }
+  }
+  const int op0 = SNAPPY ? (n < 128 ? 1 : n < 16384 ? 2 : 3) : 0;  // Snappy: varint(n) comes first
+  const int base = op0 + inc - (size0 + R.rest);                  // my first record's output offset
+  const int N = __shfl_sync(FULL, cnt, 31);
+  int total = op0 + __shfl_sync(FULL, inc, 31);
+  // 3. compaction
+  for (int t = 0; t < N; t += 32) {
+    const int i = t + lane;
+    const int ic = i < N ? i : N - 1;  // every lane takes part in the shuffles; the surplus lanes are masked at the end
+    int k = 0;                         // owner: first lane whose inclusive record count exceeds ic
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const int c = __shfl_sync(FULL, cnt, k + step - 1);
+      if (c <= ic) k += step;
+    }
+    const int j = ic - (__shfl_sync(FULL, cnt, k) - __shfl_sync(FULL, R.nrec, k));
+    const int base_k = __shfl_sync(FULL, base, k), size0_k = __shfl_sync(FULL, size0, k),
+              anc_k = __shfl_sync(FULL, anchor_in, k);
+    uint2 r = seq[(size_t)k * slot + j];
+    if (j == 0) {
+      const int pm = (int)r.x, len = (int)r.y;
+      r.x = (uint32_t)anc_k | ((uint32_t)(pm - anc_k) << 16);
+      r.y = (uint32_t)len | ((uint32_t)base_k << 16);
+    } else {
+      r.y += (uint32_t)(base_k + size0_k) << 16;
+    }
+    __syncwarp();
+    if (i < N) seq[i] = r;
+    __syncwarp();
+  }
+  // 4. final literals, counts, sizes
+  if (lane == 0) {
+    uint32_t ns = (uint32_t)N;
+    const int lit = n - anchor_f;
+    if (ZSTD) {
+      seq[ns++] = make_uint2((uint32_t)anchor_f | ((uint32_t)lit << 16), (uint32_t)total << 16);
+      nseq[b] = ns;
+    } else if (SNAPPY) {
+      if (lit) {
+        seq[ns++] = make_uint2((uint32_t)anchor_f | ((uint32_t)lit << 16), (uint32_t)total << 16);
+        total += lit + (lit - 1 < 60 ? 1 : lit - 1 < 256 ? 2 : 3);
+      }
+      nseq[b] = ns;
+      csize[b] = (uint32_t)total;
+      sizes[b] = 4u + (uint64_t)total;
+    } else {
+      seq[ns++] = make_uint2((uint32_t)anchor_f | ((uint32_t)lit << 16), (uint32_t)total << 16);
+      total += 1 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);
+      const bool fail = total > n - 1;  // LZ4BlockOutputStream stores RAW when compressedLength >= originalLength
+      nseq[b] = ns;
+      csize[b] = fail ? ((uint32_t)n | 0x80000000u) : (uint32_t)total;
+      sizes[b] = 21u + (uint64_t)(fail ? n : total);
+    }
   }
 }
 
@@ -713,7 +880,12 @@ __global__ void __launch_bounds__(kEmitThreads) lz4_emit_kernel(
 // launchers
 // ------------------------------------------------------------------------------------------------------------
 int g_lz4_hlog = 12;  // B2S_LZ4_HLOG (api.cu reads it once at init); 12 is the specified default
-int g_lz4_pipe = 2;   // B2S_LZ4_PIPE: 2 = match2 + parse2 (off[] only, extension in the parse); 1 = first generation (A/B runs)
+int g_lz4_match_depth = 1;  // B2S_LZ4_MATCH_DEPTH: windows between requesting and using the candidate words (1 or 2)
+// B2S_LZ4_PIPE: 4 = match2 + sub-chunk parallel parse (LZ4Block; Snappy and Zstandard stay on generation 1: their CPU
+// models state the single-cursor parse); 1 = first generation; 2 / 3 = match2 + thread-per-block parse with in-parse
+// extension (fixed-trip / event-driven) — measured slower, kept for A/B runs (profiles/r2a_*, r2c_*)
+int g_lz4_pipe = 4;
+static int pipe_for(uint32_t codec) { return g_lz4_pipe == 4 && codec != B2S_CODEC_LZ4BLOCK ? 1 : g_lz4_pipe; }
 
 template <int HLOG>
 static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
@@ -736,39 +908,60 @@ static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, c
 template <int HLOG>
 static void launch_match2_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                             const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
-                            uint32_t block_size, uint32_t stride, uint16_t* d_off, unsigned int* d_counter,
-                            cudaStream_t st) {
+                            uint32_t block_size, uint32_t stride, uint16_t* d_off, uint32_t* d_mask,
+                            unsigned int* d_counter, cudaStream_t st) {
   const size_t smem = (size_t)kMatchWarps * (2u << HLOG);
-  cudaFuncSetAttribute(lz4_match2_kernel<HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = g_lz4_match_depth == 2 ? lz4_match2_kernel<HLOG, 2> : lz4_match2_kernel<HLOG, 1>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_match2_kernel<HLOG>, kMatchWarps * 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMatchWarps * 32, smem);
   if (per_sm < 1) per_sm = 1;
   uint64_t want = ((uint64_t)m + kMatchWarps - 1) / kMatchWarps;
   uint64_t grid = (uint64_t)kSMs * per_sm;  // persistent: one wave, warps pull blocks from the counter
   if (grid > want) grid = want;
-  lz4_match2_kernel<HLOG><<<(unsigned)grid, kMatchWarps * 32, smem, st>>>(
-      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, d_off, d_counter);
+  kern<<<(unsigned)grid, kMatchWarps * 32, smem, st>>>(
+      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, d_off, d_mask, d_counter);
 }
 
-size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size) {
-  const size_t stride = (block_size + 31u) & ~31u;
-  const size_t max_seq = stride / 4 + 2;
-  // off + ml (4 B / position), records, and (Zstandard only, always reserved) one byte per position of bitstream
-  return (size_t)chunk_blocks * (stride * 4 + max_seq * 8 + stride + 32) + 1024;
-}
-
+// Workspace of one pass over `m` codec blocks, by pipeline generation and codec:
+//   off   u16 per position                                     (all)
+//   aux   generation 1: ml u16 per position; generation >= 2: one 32-bit match mask per window
+//   seq   8-byte records, max_seq per block                     (all)
+//   bits  one byte per position + 32: the sequence bitstream    (Zstandard only)
 struct Lz4Ws {
   uint32_t stride, max_seq;
   uint16_t *off, *ml;
+  uint32_t* mask;
   uint2* seq;
+  uint8_t* bits;
 };
-static Lz4Ws carve_ws(uint8_t* d_ws, uint32_t m, uint32_t block_size) {
+static size_t ws_aux_bytes(size_t stride, int pipe) { return pipe == 1 ? stride * 2 : stride / 8; }
+static size_t ws_max_seq(size_t stride, int pipe) {
+  // generation 4 stages 32 lists of up to S/4 records at slots of S/4 + 1 before compacting them in place
+  return pipe == 4 ? 32 * (parse4_sub((uint32_t)stride) / 4 + 1) + 2 : stride / 4 + 2;
+}
+size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size, uint32_t codec) {
+  const size_t stride = (block_size + 31u) & ~31u;
+  const int pipe = pipe_for(codec);
+  const size_t per_block = stride * 2 + ws_aux_bytes(stride, pipe) + ws_max_seq(stride, pipe) * 8 +
+                           (codec == B2S_CODEC_ZSTD ? stride + 32 : 0);
+  return (size_t)chunk_blocks * per_block + 1024;
+}
+static Lz4Ws carve_ws(uint8_t* d_ws, uint32_t m, uint32_t block_size, uint32_t codec) {
   Lz4Ws w;
+  const int pipe = pipe_for(codec);
   w.stride = (block_size + 31u) & ~31u;
-  w.max_seq = w.stride / 4 + 2;
+  w.max_seq = (uint32_t)ws_max_seq(w.stride, pipe);
+  size_t at = 0;
   w.off = reinterpret_cast<uint16_t*>(d_ws);
-  w.ml = w.off + (size_t)m * w.stride;
-  w.seq = reinterpret_cast<uint2*>(d_ws + (size_t)m * w.stride * 4);
+  at += (size_t)m * w.stride * 2;
+  w.ml = reinterpret_cast<uint16_t*>(d_ws + at);
+  w.mask = reinterpret_cast<uint32_t*>(d_ws + at);
+  at += (size_t)m * ws_aux_bytes(w.stride, pipe);
+  at = (at + 15) & ~size_t(15);
+  w.seq = reinterpret_cast<uint2*>(d_ws + at);
+  at += (size_t)m * w.max_seq * 8;
+  w.bits = d_ws + at;
   return w;
 }
 
@@ -777,31 +970,40 @@ static void launch_parse_t(const uint8_t* src_base, const uint64_t* d_src_off, c
                            const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m,
                            uint32_t block_size, const Lz4Ws& w, uint32_t* d_nseq, uint32_t* d_csize, uint64_t* d_sizes,
                            cudaStream_t st) {
-  if (g_lz4_pipe == 1)
+  const int pipe = pipe_for(CODEC == 0 ? B2S_CODEC_LZ4BLOCK : CODEC == 1 ? B2S_CODEC_SNAPPY_XERIAL : B2S_CODEC_ZSTD);
+  if (pipe == 4)
+    lz4_parse4_kernel<CODEC><<<(m + kParse4Warps - 1) / kParse4Warps, kParse4Warps * 32, 0, st>>>(
+        src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq, w.off, w.mask,
+        w.seq, d_nseq, d_csize, d_sizes);
+  else if (pipe == 1)
     lz4_parse_kernel<CODEC><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
                                                           w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
+  else if (pipe == 2)
+    lz4_parse2_kernel<CODEC, false><<<(m + 63) / 64, 64, 0, st>>>(
+        src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq, w.off,
+        w.mask, w.seq, d_nseq, d_csize, d_sizes);
   else
-    lz4_parse2_kernel<CODEC><<<(m + 63) / 64, 64, 0, st>>>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m,
-                                                           block_size, w.stride, w.max_seq, w.off, w.seq, d_nseq,
-                                                           d_csize, d_sizes);
+    lz4_parse2_kernel<CODEC, true><<<(m + 63) / 64, 64, 0, st>>>(
+        src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq, w.off,
+        w.mask, w.seq, d_nseq, d_csize, d_sizes);
 }
 
 void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                       const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
                       uint32_t codec, uint8_t* d_ws, unsigned int* d_counter, cudaStream_t st, uint64_t* launches,
-                      cudaEvent_t ev0, cudaEvent_t ev1) {
+                      cudaEvent_t ev0, cudaEvent_t ev1, int hlog) {
   if (!m) return;
   const uint32_t near_limit = codec == B2S_CODEC_SNAPPY_XERIAL ? 2048u : 0u;
-  const Lz4Ws w = carve_ws(d_ws, m, block_size);
+  const Lz4Ws w = carve_ws(d_ws, m, block_size, codec);
   cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), st);
   if (ev0) cudaEventRecord(ev0, st);
 #define B2S_LZ4M(H)                                                                                                    \
-  (g_lz4_pipe == 1                                                                                                     \
+  (pipe_for(codec) == 1                                                                                                \
        ? launch_match_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,         \
                            near_limit, w.off, w.ml, d_counter, st)                                                     \
        : launch_match2_t<H>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.off, \
-                            d_counter, st))
-  switch (g_lz4_hlog) {
+                            w.mask, d_counter, st))
+  switch (hlog > 0 ? hlog : g_lz4_hlog) {
     case 10: B2S_LZ4M(10); break;
     case 11: B2S_LZ4M(11); break;
     case 13: B2S_LZ4M(13); break;
@@ -819,10 +1021,10 @@ void launch_lz4_parse_emit(const uint8_t* src_base, const uint64_t* d_src_off, c
                            uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches,
                            cudaEvent_t ev_parsed) {
   if (!m) return;
-  const Lz4Ws w = carve_ws(d_ws, m, block_size);
+  const Lz4Ws w = carve_ws(d_ws, m, block_size, codec);
   if (codec == B2S_CODEC_ZSTD) {
     launch_parse_t<2>(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w, d_nseq, d_csize, d_sizes, st);
-    uint8_t* d_bits = d_ws + (size_t)m * w.stride * 4 + (size_t)m * w.max_seq * 8;
+    uint8_t* d_bits = w.bits;
     // d_hash is unused by this codec and carries the bitstream sizes from the entropy stage to the emit kernel
     launch_zstd_seqenc(src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq,
                        w.off, w.seq, d_nseq, d_bits, const_cast<uint32_t*>(d_hash), d_csize, d_sizes, st, launches);

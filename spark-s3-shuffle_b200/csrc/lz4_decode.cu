@@ -17,10 +17,13 @@
 //                         short matches are copied by their lanes, long ones by the whole warp.
 #include "kernels.h"
 #include "lz_batch.cuh"
+#include "tma_ring.cuh"
 
 namespace b2s {
 
 constexpr int kMinMatch = 4, kMFLimit = 12, kLastLiterals = 5;
+int g_lz4d_copy_group = 1;  // B2S_LZ4D_COPYGROUP: bytes of a short match per trip in the copy kernel (1 or 4)
+int g_lz4d_tokens = 1;  // B2S_LZ4D_TOKENS: 1 = global loads + L1 prefetch, 2 = TMA ring (tma_ring.cuh)
 
 // record: x = literal count | match length << 16 (0 = final sequence) ; y = offset | literal source position << 16
 __global__ void __launch_bounds__(64) lz4_tokens_kernel(const BlockDesc* __restrict__ desc, uint32_t b0, uint32_t m,
@@ -138,7 +141,129 @@ __global__ void __launch_bounds__(64) lz4_tokens_kernel(const BlockDesc* __restr
   nrec[b] = ns;
 }
 
+// The same walk with the compressed stream arriving through the TMA ring of tma_ring.cuh (B2S_LZ4D_TOKENS=2): the
+// stream is requested in 64-byte bulk copies four pieces ahead of the cursor and read from shared memory — no global
+// load instruction in the token chain, no prefetch bookkeeping.  Literal bytes are skipped over, not read; pieces the
+// walk jumps across are still fetched (the ring is strictly sequential) but never waited for longer than they take.
+constexpr int kTokThreads = 64;
+__global__ void __launch_bounds__(kTokThreads) lz4_tokens_tma_kernel(const BlockDesc* __restrict__ desc, uint32_t b0,
+                                                                     uint32_t m, const uint8_t* __restrict__ src_base,
+                                                                     uint2* __restrict__ rec, uint32_t rec_stride,
+                                                                     uint32_t* __restrict__ nrec,
+                                                                     int32_t* __restrict__ status) {
+  __shared__ __align__(128) uint8_t s_ring[kTokThreads * kRingBytes];
+  __shared__ __align__(8) uint64_t s_bars[kTokThreads * kRingStages];
+  const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= m) return;
+  const uint32_t b = b0 + bl;
+  const BlockDesc d = desc[b];
+  if (d.olen == 0 || (d.stream & 0x80000000u)) {  // no-op descriptor or stored RAW (copied by P2)
+    nrec[b] = 0;
+    return;
+  }
+  const uint8_t* __restrict__ in = src_base + d.src;
+  const int clen = (int)d.clen, olen = (int)d.olen;
+  uint2* __restrict__ r = rec + (size_t)bl * rec_stride;
+  TmaRing R;
+  R.init(s_ring + threadIdx.x * kRingBytes, s_bars + threadIdx.x * kRingStages, in, clen);
+  const int sh0 = (int)(reinterpret_cast<uintptr_t>(in) & 15u);  // stream position of block byte 0
+  int ip = 0, op = 0;
+  uint32_t ns = 0;
+  bool err = false;
+  while (true) {
+    if (ip >= clen) {
+      err = true;
+      break;
+    }
+    // window: bytes ip .. ip+7 from three aligned words of the ring (bytes past the block's end are never used)
+    const int u = sh0 + ip;
+    R.consume_to(u);
+    R.ensure(u + 11);
+    const int w = u & ~3;
+    const unsigned wsh = (unsigned)(u & 3) * 8u;
+    const uint32_t x0 = R.word(w), x1 = R.word(w + 4), x2 = R.word(w + 8);
+    const uint32_t lo = __funnelshift_r(x0, x1, wsh), hi = __funnelshift_r(x1, x2, wsh);
+    const int token = (int)(lo & 0xffu);
+    ip++;
+    int ll = token >> 4;
+    if (ll == 15) {
+      int bb;
+      do {
+        if (ip >= clen) {
+          err = true;
+          break;
+        }
+        R.ensure(sh0 + ip);
+        bb = (int)R.byte(sh0 + ip);
+        ip++;
+        ll += bb;
+      } while (bb == 255);
+      if (err) break;
+    }
+    if (ll > olen - op || ll > clen - ip) {
+      err = true;
+      break;
+    }
+    const int lit_ip = ip;
+    ip += ll;
+    op += ll;
+    if (olen - op < kMFLimit) {  // last sequence: literals only; a match may not start < 12 bytes before the end
+      if (op != olen || ip != clen) err = true;
+      else r[ns++] = make_uint2((uint32_t)ll, (uint32_t)lit_ip << 16);
+      break;
+    }
+    if (ip + 2 > clen) {
+      err = true;
+      break;
+    }
+    int off;
+    if (ll <= 5 && (token >> 4) != 15) {  // offset bytes sit at window bytes 1+ll, 2+ll (<= 7)
+      const unsigned sb = 8u * (unsigned)(1 + ll);
+      const uint32_t wv = sb < 32 ? __funnelshift_r(lo, hi, sb) : hi >> (sb - 32);
+      off = (int)(wv & 0xffffu);
+    } else {
+      R.consume_to(sh0 + ip);
+      R.ensure(sh0 + ip + 1);
+      off = (int)(R.byte(sh0 + ip) | (R.byte(sh0 + ip + 1) << 8));
+    }
+    ip += 2;
+    int ml = token & 15;
+    if (ml == 15) {
+      int bb;
+      do {
+        if (ip >= clen) {
+          err = true;
+          break;
+        }
+        R.ensure(sh0 + ip);
+        bb = (int)R.byte(sh0 + ip);
+        ip++;
+        ml += bb;
+      } while (bb == 255);
+      if (err) break;
+    }
+    ml += kMinMatch;
+    if (ml > olen - op || off == 0 || off > op) {
+      err = true;
+      break;
+    }
+    r[ns++] = make_uint2((uint32_t)ll | ((uint32_t)ml << 16), (uint32_t)off | ((uint32_t)lit_ip << 16));
+    op += ml;
+    if (olen - op < kLastLiterals) {  // the last 5 bytes of a block are literals
+      err = true;
+      break;
+    }
+  }
+  R.drain();
+  if (err) {
+    set_status(status, d.stream & 0x7fffffffu, B2S_E_CORRUPT);
+    ns = 0;
+  }
+  nrec[b] = ns;
+}
+
 constexpr int kCopyThreads = 256;
+template <int GROUP>
 __global__ void __launch_bounds__(kCopyThreads) lz4_copy_kernel(const BlockDesc* __restrict__ desc, uint32_t b0,
                                                                 uint32_t m, const uint8_t* __restrict__ src_base,
                                                                 uint8_t* dst_base, const uint2* __restrict__ rec,
@@ -192,7 +317,7 @@ __global__ void __launch_bounds__(kCopyThreads) lz4_copy_kernel(const BlockDesc*
     __syncwarp();
 
     // ---- matches, in dependency rounds (lz_batch.cuh)
-    lz_execute_matches(out, op + lit, ml, off, lane);
+    lz_execute_matches<GROUP>(out, op + lit, ml, off, lane);
   }
 }
 
@@ -216,6 +341,10 @@ void launch_lz4_tokens(uint32_t codec, const BlockDesc* d_desc, uint32_t b0, uin
   uint2* rec = reinterpret_cast<uint2*>(d_ws);
   if (codec == B2S_CODEC_SNAPPY_XERIAL) {
     launch_snappy_tokens(d_desc, b0, m, src_base, rec, rec_stride, d_nrec, d_status, st, launches);
+  } else if (g_lz4d_tokens == 2) {
+    lz4_tokens_tma_kernel<<<(m + kTokThreads - 1) / kTokThreads, kTokThreads, 0, st>>>(d_desc, b0, m, src_base, rec,
+                                                                                     rec_stride, d_nrec, d_status);
+    *launches += 1;
   } else {
     lz4_tokens_kernel<<<(m + 63) / 64, 64, 0, st>>>(d_desc, b0, m, src_base, rec, rec_stride, d_nrec, d_status);
     *launches += 1;
@@ -225,8 +354,12 @@ void launch_lz4_copy(const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t 
                      uint8_t* dst_base, const uint8_t* d_ws, const uint32_t* d_nrec, cudaStream_t st,
                      uint64_t* launches) {
   if (!m) return;
-  lz4_copy_kernel<<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
-      d_desc, b0, m, src_base, dst_base, reinterpret_cast<const uint2*>(d_ws), rec_stride, d_nrec);
+  if (g_lz4d_copy_group == 4)
+    lz4_copy_kernel<4><<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
+        d_desc, b0, m, src_base, dst_base, reinterpret_cast<const uint2*>(d_ws), rec_stride, d_nrec);
+  else
+    lz4_copy_kernel<1><<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
+        d_desc, b0, m, src_base, dst_base, reinterpret_cast<const uint2*>(d_ws), rec_stride, d_nrec);
   *launches += 1;
 }
 

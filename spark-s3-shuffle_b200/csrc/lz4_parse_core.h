@@ -227,5 +227,282 @@ B2S_PHD Result parse_block(const Mem& mem, int n, int sb, uint32_t stride, uint2
   return r;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Event-driven variant (B2S_LZ4_PIPE=3).  The fixed-trip walk above visits every group of four positions (8192 per
+// 32 KiB block) and, because the 32 lanes of a warp sit in different phases, pays every path of its body each time
+// (ncu: ~130 warp-instructions per group).  This variant iterates per EVENT instead: the match kernel also stores one
+// 32-bit word per window with a bit per matched position, so "next match at or after the cursor" is a find-first-set,
+// and an iteration is "take the next match (one off[] gather) and/or compare eight more bytes of the open match, emit
+// if it closed".  A sequence flagged "exactly 4" costs one iteration, a longer one 1 + (len - 4) / 8; empty windows
+// cost one cheap iteration each.  Same sequences, same records as parse_block().
+// Mem additionally provides mask(w) (window w's match bits), off16(q) and word(k) without the ring.
+template <int CODEC, class Mem>
+B2S_PHD Result parse_block_ev(const Mem& mem, int n, int sb, uint32_t stride, uint2* seq) {
+  constexpr bool SNAPPY = CODEC == 1, ZSTD = CODEC == 2;
+  const bool flag4 = stride <= 32768u;
+  const uint32_t omask = flag4 ? 0x7fffu : 0xffffu;
+  int anchor = 0, op = SNAPPY ? (n < 128 ? 1 : n < 16384 ? 2 : 3) : 0;
+  uint2* sp = seq;  // next record
+  const int mflimit = n - kMFLimit, matchlimit = n - kLastLiterals;
+  // LZ4: the RAW decision (compressedLength >= originalLength) is taken once at the end — op only grows, and a block
+  // that fails it is re-emitted from the source, its records are ignored (op may then exceed the record's 16 bits)
+
+  if (n >= kMFLimit + 1) {
+    const int last_w = mflimit >> 5;
+    int wi = 0;
+    uint32_t mw = mem.mask(0);
+    // pm < 0: searching; otherwise the open match starts at pm, offset ed, next byte to compare e (x4: nothing to compare)
+    int pm = -1, ed = 0, e = 0;
+    bool x4 = false, done = false;
+    while (!(done && pm < 0)) {
+      if (pm < 0) {
+        if (mw == 0u) {
+          wi++;
+          if (wi > last_w) done = true;
+          else mw = mem.mask(wi);
+        } else {
+          pm = (wi << 5) + first_set(mw);
+          const uint32_t o16 = mem.off16(pm);
+          ed = (int)(o16 & omask);
+          e = pm + 4;
+          x4 = flag4 && (o16 & 0x8000u);
+        }
+      }
+      if (pm >= 0) {
+        int eq = 0;
+        bool end = true;
+        if (!x4) {
+          // eight bytes at e against the eight at e - ed: three aligned words each; only the source side can run past
+          // the block's last word (clamped; the surplus bytes are cut off by room)
+          const int ci = sb + e, cj = ci - ed;
+          const unsigned sha = (unsigned)(ci & 3) * 8u, shc = (unsigned)(cj & 3) * 8u;
+          const int ka = ci >> 2, kc = cj >> 2;
+          const uint32_t a0 = mem.cand_word(ka), a1 = mem.word(ka + 1), a2 = mem.word(ka + 2);
+          const uint32_t c0 = mem.cand_word(kc), c1 = mem.cand_word(kc + 1), c2 = mem.cand_word(kc + 2);
+          const uint32_t xl = funnel_r(a0, a1, sha) ^ funnel_r(c0, c1, shc);
+          const uint32_t xh = funnel_r(a1, a2, sha) ^ funnel_r(c1, c2, shc);
+          eq = xl ? (first_set(xl) >> 3) : xh ? 4 + (first_set(xh) >> 3) : 8;
+          const int room = matchlimit - e;  // > 0
+          eq = eq < room ? eq : room;
+          end = eq < 8 || eq == room;
+        }
+        if (end) {
+          const int len = e + eq - pm;
+          const int lit = pm - anchor;
+          int size;
+          if (ZSTD) {
+            size = lit;
+          } else if (SNAPPY) {
+            size = lit ? lit + (lit - 1 < 60 ? 1 : lit - 1 < 256 ? 2 : 3) : 0;
+            int l = len;
+            if (l >= 68) {
+              const int k = (l - 68) / 64 + 1;
+              size += 3 * k;
+              l -= 64 * k;
+            }
+            if (l > 64) {
+              size += 3;
+              l -= 60;
+            }
+            size += (l < 12 && ed < 2048) ? 2 : 3;
+          } else {
+            const int mlc = len - kMinMatch;
+            size = 3 + lit;
+            if (lit >= 15) size += (lit - 15) / 255 + 1;
+            if (mlc >= 15) size += (mlc - 15) / 255 + 1;
+          }
+          *sp++ = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)len | ((uint32_t)op << 16));
+          op += size;
+          const int p = pm + len;
+          anchor = p;
+          pm = -1;
+          const int nw = p >> 5;
+          if (nw != wi) {
+            wi = nw;
+            if (wi > last_w) {
+              done = true;
+              mw = 0u;
+            } else {
+              mw = mem.mask(wi);
+            }
+          }
+          mw &= ~0u << (p & 31);
+        } else {
+          e += 8;
+        }
+      }
+    }
+  }
+  Result r;
+  if (ZSTD) {
+    *sp++ = make_uint2((uint32_t)anchor | ((uint32_t)(n - anchor) << 16), (uint32_t)op << 16);
+    r.nseq = (uint32_t)(sp - seq);
+    r.csize = 0;
+    r.size = 0;
+    return r;
+  }
+  if (SNAPPY) {
+    const int lit = n - anchor;
+    if (lit) {
+      *sp++ = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)op << 16);
+      op += lit + (lit - 1 < 60 ? 1 : lit - 1 < 256 ? 2 : 3);
+    }
+    r.nseq = (uint32_t)(sp - seq);
+    r.csize = (uint32_t)op;
+    r.size = 4u + (uint64_t)op;
+    return r;
+  }
+  {
+    const int lit = n - anchor;
+    *sp++ = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)op << 16);
+    op += 1 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);
+  }
+  const bool fail = op > n - 1;
+  r.nseq = (uint32_t)(sp - seq);
+  r.csize = fail ? ((uint32_t)n | 0x80000000u) : (uint32_t)op;
+  r.size = 21u + (uint64_t)(fail ? n : op);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sub-chunk parallel parse (B2S_LZ4_PIPE=4, the default).  Both thread-per-block walks above are bound by the LATENCY
+// of one thread's chain over 32 KiB (ncu, profiles/r2c_*: the event-driven walk executes 40 % fewer instructions than
+// the fixed-trip one and is slower, 9.5 ms per 32,768 blocks at 8 % issue utilisation — every iteration ends in
+// dependent loads).  The fix is parallelism INSIDE the block: the block is cut into 32 sub-chunks of S = stride / 32
+// positions (1 KiB for 32 KiB blocks), lane k of a WARP parses sub-chunk k greedily from its first position, and a match
+// neither starts in the last three positions of a sub-chunk nor extends past its end.  That is a (slightly) different
+// compressor — at most one cut match per KiB, ~0.5 % more output on the terasort shape — so the executable
+// specification in oracle/ states the same rule (orc_lz4_compress_block_win, `sub`), and the bytes still have to agree.
+// The warp then stitches the 32 record lists together (lz4_parse4_kernel: literal runs that span sub-chunks, output
+// offsets by warp scans, in-place compaction of the staged records); 32,768 warps instead of 1,024 per GiB hide the
+// latency this walk cannot avoid.
+//
+// walk_subchunk(): lane-local part, host/device.  Records are staged at `stage[0..]` in the final format except that
+// offsets are relative to the sub-chunk's first record and record 0 carries its match position instead of an anchor:
+//   record 0 : x = pm0                    y = len0
+//   record i : x = anchor | lit << 16     y = len | rel_op << 16    (rel_op = sum of the sizes of records 1..i-1)
+struct SubResult {
+  int nrec;       // records staged
+  int rest;       // sum of the sizes of records 1..nrec-1 (CODEC 2: their literal bytes)
+  int pm0, len0, d0;  // first match of the sub-chunk (valid if nrec > 0)
+  int last_end;   // end of the last match, -1 if none
+};
+
+template <int CODEC>
+B2S_PHD int seq_size(int lit, int len, int d) {
+  constexpr bool SNAPPY = CODEC == 1, ZSTD = CODEC == 2;
+  if (ZSTD) return lit;
+  if (SNAPPY) {
+    int size = lit ? lit + (lit - 1 < 60 ? 1 : lit - 1 < 256 ? 2 : 3) : 0;
+    int l = len;
+    if (l >= 68) {
+      const int k = (l - 68) / 64 + 1;
+      size += 3 * k;
+      l -= 64 * k;
+    }
+    if (l > 64) {
+      size += 3;
+      l -= 60;
+    }
+    return size + ((l < 12 && d < 2048) ? 2 : 3);
+  }
+  const int mlc = len - kMinMatch;
+  int size = 3 + lit;
+  if (lit >= 15) size += (lit - 15) / 255 + 1;
+  if (mlc >= 15) size += (mlc - 15) / 255 + 1;
+  return size;
+}
+
+template <int CODEC, class Mem>
+B2S_PHD SubResult walk_subchunk(const Mem& mem, int n, int sb, uint32_t stride, int lo, int hi, uint2* stage) {
+  const bool flag4 = stride <= 32768u;
+  const uint32_t omask = flag4 ? 0x7fffu : 0xffffu;
+  SubResult R;
+  R.nrec = 0;
+  R.rest = 0;
+  R.pm0 = R.len0 = R.d0 = 0;
+  R.last_end = -1;
+  const int mflimit = n - kMFLimit, matchlimit = n - kLastLiterals;
+  const int plim = mflimit < hi - 4 ? mflimit : hi - 4;       // last position a match may start at
+  const int elim = matchlimit < hi ? matchlimit : hi;         // a match ends at or before this position
+  if (lo > plim) return R;
+  const int last_w = plim >> 5;
+  int wi = lo >> 5;
+  uint32_t mw = mem.mask(wi);
+  int pm = -1, ed = 0, e = 0, anchor = lo, rel = 0;
+  bool x4 = false, done = false;
+  uint2* sp = stage;
+  while (!(done && pm < 0)) {
+    if (pm < 0) {
+      if (mw == 0u) {
+        wi++;
+        if (wi > last_w) done = true;
+        else mw = mem.mask(wi);
+      } else {
+        const int q = (wi << 5) + first_set(mw);
+        if (q > plim) {
+          done = true;
+        } else {
+          pm = q;
+          const uint32_t o16 = mem.off16(q);
+          ed = (int)(o16 & omask);
+          e = q + 4;
+          x4 = (flag4 && (o16 & 0x8000u)) || e >= elim;  // nothing (more) to compare
+        }
+      }
+    }
+    if (pm >= 0) {
+      int eq = 0;
+      bool end = true;
+      if (!x4) {
+        const int ci = sb + e, cj = ci - ed;
+        const unsigned sha = (unsigned)(ci & 3) * 8u, shc = (unsigned)(cj & 3) * 8u;
+        const int ka = ci >> 2, kc = cj >> 2;
+        const uint32_t a0 = mem.cand_word(ka), a1 = mem.word(ka + 1), a2 = mem.word(ka + 2);
+        const uint32_t c0 = mem.cand_word(kc), c1 = mem.cand_word(kc + 1), c2 = mem.cand_word(kc + 2);
+        const uint32_t xl = funnel_r(a0, a1, sha) ^ funnel_r(c0, c1, shc);
+        const uint32_t xh = funnel_r(a1, a2, sha) ^ funnel_r(c1, c2, shc);
+        eq = xl ? (first_set(xl) >> 3) : xh ? 4 + (first_set(xh) >> 3) : 8;
+        const int room = elim - e;  // > 0
+        eq = eq < room ? eq : room;
+        end = eq < 8 || eq == room;
+      }
+      if (end) {
+        const int len = e + eq - pm;
+        if (sp == stage) {
+          R.pm0 = pm;
+          R.len0 = len;
+          R.d0 = ed;
+          *sp++ = make_uint2((uint32_t)pm, (uint32_t)len);
+        } else {
+          const int lit = pm - anchor;
+          *sp++ = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)len | ((uint32_t)rel << 16));
+          rel += seq_size<CODEC>(lit, len, ed);
+        }
+        const int p = pm + len;
+        anchor = p;
+        pm = -1;
+        const int nw = p >> 5;
+        if (nw != wi) {
+          wi = nw;
+          if (wi > last_w) {
+            done = true;
+            mw = 0u;
+          } else {
+            mw = mem.mask(wi);
+          }
+        }
+        mw &= ~0u << (p & 31);
+      } else {
+        e += 8;
+      }
+    }
+  }
+  R.nrec = (int)(sp - stage);
+  R.rest = rel;
+  R.last_end = R.nrec ? anchor : -1;
+  return R;
+}
+
 }  // namespace lzparse
 }  // namespace b2s

@@ -147,6 +147,7 @@ class S3ShuffleDispatcher {
     shuffleCompress = getBool("spark.shuffle.compress", true);
     codecName = get("spark.io.compression.codec", "lz4");
     lz4BlockSize = (uint32_t)getSize("spark.io.compression.lz4.blockSize", 32 * 1024);
+    zstdLevel = getInt("spark.io.compression.zstd.level", 1);  // Spark's default [U]; reaches b2s_compress_* as `level`
     gpuEnabled = getBool("spark.shuffle.s3.gpu.enabled", true);  // additive key
     gpuCodecBufferSize = (uint64_t)getSize("spark.shuffle.s3.gpu.codecBufferSize", 64L * 1024 * 1024);  // additive
     gpuReadBatchBlocks = getInt("spark.shuffle.s3.gpu.readBatchBlocks", 0);  // additive; 0 = all completed blocks
@@ -196,6 +197,7 @@ class S3ShuffleDispatcher {
        gpuEnabled = true;
   int bufferSize = 0, maxBufferSizeTask = 0, maxConcurrencyTask = 0, folderPrefixes = 10;
   uint32_t lz4BlockSize = 32768;
+  int zstdLevel = 1;
   uint64_t gpuCodecBufferSize = 64ull << 20;
   int gpuReadBatchBlocks = 0;
   bool gpuCoalesce = false;
@@ -398,6 +400,7 @@ class S3ShuffleMapOutputWriter {
         r.op = 0;
         r.codec = (uint32_t)d_.codecId();
         r.block_size = d_.lz4BlockSize;
+        r.level = d_.zstdLevel;
         r.checksum_alg = alg;
         r.n = n;
         r.src = sp.data();
@@ -410,7 +413,7 @@ class S3ShuffleMapOutputWriter {
         submit_or_throw(d_.queue, r, "b2s_compress_batch");
         for (uint32_t k = 0; k < n; k++) total += dlen[k];
       } else {
-        int rc = b2s_compress_packed((uint32_t)d_.codecId(), 0, d_.lz4BlockSize, alg, n, data, off.data(), len.data(),
+        int rc = b2s_compress_packed((uint32_t)d_.codecId(), d_.zstdLevel, d_.lz4BlockSize, alg, n, data, off.data(), len.data(),
                                      out_.data(), bound, doff.data(), dlen.data(), &total, cks.data(), status.data());
         if (rc != 0) throw CodecException(std::string("b2s_compress_packed: ") + b2s_strerror(rc) + ": " + b2s_last_error());
       }

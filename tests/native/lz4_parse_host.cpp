@@ -17,8 +17,9 @@ namespace {
 
 uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 
-void match_model(const uint8_t* s, int n, int hash_log, uint32_t stride, uint16_t* off) {
+void match_model(const uint8_t* s, int n, int hash_log, uint32_t stride, uint16_t* off, uint32_t* mask) {
   memset(off, 0xEE, stride * 2);  // rows are reused between chunks: whatever the match kernel does not write is garbage
+  memset(mask, 0xEE, stride / 8);
   if (n < 13) return;
   const int mflimit = n - 12;
   std::vector<uint16_t> table((size_t)1 << hash_log, 0);
@@ -34,12 +35,17 @@ void match_model(const uint8_t* s, int n, int hash_log, uint32_t stride, uint16_
         if (flag4 && o && s[p + 4] != s[p + 4 - o]) o |= 0x8000u;
       }
       off[p] = (uint16_t)o;  // the kernel stores all 32 lanes of the window (invalid positions: 0)
+      if (p == pos) mask[pos >> 5] = 0;
+      if (o) mask[pos >> 5] |= 1u << (p - pos);  // the window's match bits (one word per window)
     }
     for (int p = pos; p < pos + 32 && p <= mflimit; p++) table[(rd32(s + p) * 2654435761u) >> (32 - hash_log)] = (uint16_t)p;
   }
 }
 
 struct MemHost {
+  const uint32_t* maskrow;
+  uint32_t mask(int w) const { return maskrow[w]; }
+  uint32_t off16(int q) const { return off[q]; }
   const uint16_t* off;
   const uint8_t* aligned;  // 4-byte aligned start of the word stream
   int ovmax, kmax;
@@ -73,13 +79,22 @@ int ph_parse(int codec, const unsigned char* src, int n, int sb, int hash_log, u
   uint8_t* base = reinterpret_cast<uint8_t*>(store.data());
   memcpy(base + sb, src, (size_t)n);
   std::vector<uint16_t> off(stride ? stride : 32);
-  match_model(base + sb, n, hash_log, stride ? stride : 32, off.data());
-  MemHost mem{off.data(), base, (int)((stride ? stride : 32) >> 3) - 1, n > 0 ? (sb + n - 1) >> 2 : 0};
+  std::vector<uint32_t> mask((stride ? stride : 32) / 32);
+  match_model(base + sb, n, hash_log, stride ? stride : 32, off.data(), mask.data());
+  MemHost mem{mask.data(), off.data(), base, (int)((stride ? stride : 32) >> 3) - 1, n > 0 ? (sb + n - 1) >> 2 : 0};
   std::vector<uint2> seq((size_t)stride / 4 + 2);
   b2s::lzparse::Result r;
-  if (codec == 0) r = b2s::lzparse::parse_block<0>(mem, n, sb, stride, seq.data());
-  else if (codec == 1) r = b2s::lzparse::parse_block<1>(mem, n, sb, stride, seq.data());
-  else r = b2s::lzparse::parse_block<2>(mem, n, sb, stride, seq.data());
+  const bool ev = codec >= 10;  // 10..12: the event-driven variant
+  codec %= 10;
+  if (ev) {
+    if (codec == 0) r = b2s::lzparse::parse_block_ev<0>(mem, n, sb, stride, seq.data());
+    else if (codec == 1) r = b2s::lzparse::parse_block_ev<1>(mem, n, sb, stride, seq.data());
+    else r = b2s::lzparse::parse_block_ev<2>(mem, n, sb, stride, seq.data());
+  } else {
+    if (codec == 0) r = b2s::lzparse::parse_block<0>(mem, n, sb, stride, seq.data());
+    else if (codec == 1) r = b2s::lzparse::parse_block<1>(mem, n, sb, stride, seq.data());
+    else r = b2s::lzparse::parse_block<2>(mem, n, sb, stride, seq.data());
+  }
   *nseq = r.nseq;
   *csize = r.csize;
   *size = r.size;
@@ -95,4 +110,91 @@ int ph_parse(int codec, const unsigned char* src, int n, int sb, int hash_log, u
   }
   return 0;
 }
+}
+
+// Generation 4: walk_subchunk() for the 32 lanes of a warp, then the kernel's stitch (lz4_parse4_kernel steps 1-4)
+// restated with plain loops.  stride / S exactly as the kernel derives them from the codec block size.
+extern "C" int ph_parse4(int codec, const unsigned char* src, int n, int sb, int hash_log, unsigned block_size,
+                         unsigned int* nseq, unsigned int* csize, unsigned long long* size, unsigned int* records) {
+  using namespace b2s::lzparse;
+  const uint32_t stride = (block_size + 31u) & ~31u;
+  const int S = (int)(((stride >> 5) + 31u) & ~31u), slot = S / 4 + 1;
+  std::vector<uint32_t> store((size_t)n / 4 + 4, 0xA5A5A5A5u);
+  uint8_t* base = reinterpret_cast<uint8_t*>(store.data());
+  memcpy(base + sb, src, (size_t)n);
+  std::vector<uint16_t> off(stride);
+  std::vector<uint32_t> mask(stride / 32);
+  match_model(base + sb, n, hash_log, stride, off.data(), mask.data());
+  MemHost mem{mask.data(), off.data(), base, (int)(stride >> 3) - 1, n > 0 ? (sb + n - 1) >> 2 : 0};
+  std::vector<uint2> seq((size_t)32 * slot + 2);
+  SubResult R[32];
+  for (int k = 0; k < 32; k++) {
+    R[k] = SubResult{0, 0, 0, 0, 0, -1};
+    const int lo = k * S;
+    if (n >= 13 && lo < n) {
+      const int hi = lo + S < n ? lo + S : n;
+      if (codec == 0) R[k] = walk_subchunk<0>(mem, n, sb, stride, lo, hi, seq.data() + (size_t)k * slot);
+      else if (codec == 1) R[k] = walk_subchunk<1>(mem, n, sb, stride, lo, hi, seq.data() + (size_t)k * slot);
+      else R[k] = walk_subchunk<2>(mem, n, sb, stride, lo, hi, seq.data() + (size_t)k * slot);
+    }
+  }
+  int anchor_in[32], size0[32], basek[32], nb[32];
+  int amax = -1, total = codec == 1 ? (n < 128 ? 1 : n < 16384 ? 2 : 3) : 0, N = 0;
+  for (int k = 0; k < 32; k++) {
+    anchor_in[k] = amax < 0 ? 0 : amax;
+    if (R[k].last_end > amax) amax = R[k].last_end;
+    size0[k] = 0;
+    if (R[k].nrec) {
+      const int lit = R[k].pm0 - anchor_in[k];
+      size0[k] = codec == 0 ? seq_size<0>(lit, R[k].len0, R[k].d0) : codec == 1 ? seq_size<1>(lit, R[k].len0, R[k].d0)
+                                                                                : seq_size<2>(lit, R[k].len0, R[k].d0);
+    }
+    basek[k] = total;
+    nb[k] = N;
+    total += size0[k] + R[k].rest;
+    N += R[k].nrec;
+  }
+  const int anchor_f = amax < 0 ? 0 : amax;
+  std::vector<uint2> dense((size_t)N + 1);
+  for (int k = 0; k < 32; k++)
+    for (int j = 0; j < R[k].nrec; j++) {
+      uint2 r = seq[(size_t)k * slot + j];
+      if (j == 0) {
+        const int pm = (int)r.x, len = (int)r.y;
+        r.x = (uint32_t)anchor_in[k] | ((uint32_t)(pm - anchor_in[k]) << 16);
+        r.y = (uint32_t)len | ((uint32_t)basek[k] << 16);
+      } else {
+        r.y += (uint32_t)(basek[k] + size0[k]) << 16;
+      }
+      dense[(size_t)nb[k] + j] = r;
+    }
+  uint32_t ns = (uint32_t)N;
+  const int lit = n - anchor_f;
+  if (codec == 2) {
+    dense[ns++] = make_uint2((uint32_t)anchor_f | ((uint32_t)lit << 16), (uint32_t)total << 16);
+    *csize = 0;
+    *size = 0;
+  } else if (codec == 1) {
+    if (lit) {
+      dense[ns++] = make_uint2((uint32_t)anchor_f | ((uint32_t)lit << 16), (uint32_t)total << 16);
+      total += lit + (lit - 1 < 60 ? 1 : lit - 1 < 256 ? 2 : 3);
+    }
+    *csize = (uint32_t)total;
+    *size = 4u + (uint64_t)total;
+  } else {
+    dense[ns++] = make_uint2((uint32_t)anchor_f | ((uint32_t)lit << 16), (uint32_t)total << 16);
+    total += 1 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);
+    const bool fail = total > n - 1;
+    *csize = fail ? ((uint32_t)n | 0x80000000u) : (uint32_t)total;
+    *size = 21u + (uint64_t)(fail ? n : total);
+  }
+  *nseq = ns;
+  const uint32_t omask = stride <= 32768u ? 0x7fffu : 0xffffu;
+  for (uint32_t i = 0; i < ns; i++) {
+    records[2 * i] = dense[i].x;
+    records[2 * i + 1] = dense[i].y;
+    const uint32_t anchor = dense[i].x & 0xffffu, l = dense[i].x >> 16, ml = dense[i].y & 0xffffu;
+    records[2 * (size_t)(n / 4 + 34) + i] = ml ? (off[anchor + l] & omask) : 0;
+  }
+  return 0;
 }

@@ -92,8 +92,15 @@ void win_find_offsets(const uint8_t* src, int n, int hash_log, std::vector<uint1
 }
 }  // namespace
 
+extern "C" long long zc_compress_model_hlog(const unsigned char* src, unsigned long long n, unsigned block_size,
+                                            unsigned char* dst, unsigned long long cap, int hash_log);
 extern "C" long long zc_compress_model(const unsigned char* src, unsigned long long n, unsigned block_size,
                                        unsigned char* dst, unsigned long long cap) {
+  return zc_compress_model_hlog(src, n, block_size, dst, cap, 12);
+}
+// hash_log: 12 = unspecified level / level 2; level 1 -> 11, level >= 3 -> 13 (hlog_for_level in csrc/api.cu)
+extern "C" long long zc_compress_model_hlog(const unsigned char* src, unsigned long long n, unsigned block_size,
+                                            unsigned char* dst, unsigned long long cap, int hash_log) {
   using namespace b2s::zstdenc;
   static CTables T;
   static bool built = false;
@@ -114,7 +121,7 @@ extern "C" long long zc_compress_model(const unsigned char* src, unsigned long l
     int anchor = 0;
     if (bn >= 13) {
       std::vector<uint16_t> off((size_t)bn, 0);
-      win_find_offsets(s, bn, 12, off);
+      win_find_offsets(s, bn, hash_log, off);
       const int mflimit = bn - 12, matchlimit = bn - 5;
       int p = 0;
       while (p <= mflimit) {

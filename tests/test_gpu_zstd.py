@@ -89,12 +89,13 @@ def zmodel(tmp_path_factory):
                            os.path.join(root, "tests", "native", "zstd_core_host.cpp")])
     L = C.CDLL(out)
     L.zc_compress_model.restype = C.c_longlong
-    L.zc_compress_model.argtypes = [C.c_char_p, C.c_ulonglong, C.c_uint, C.c_char_p, C.c_ulonglong]
+    L.zc_compress_model_hlog.restype = C.c_longlong
+    L.zc_compress_model_hlog.argtypes = [C.c_char_p, C.c_ulonglong, C.c_uint, C.c_char_p, C.c_ulonglong, C.c_int]
 
-    def model(data, block_size=32768):
+    def model(data, block_size=32768, hash_log=12):
         cap = len(data) + len(data) // 64 + 1024
         buf = C.create_string_buffer(cap)
-        n = L.zc_compress_model(data, len(data), block_size, buf, cap)
+        n = L.zc_compress_model_hlog(data, len(data), block_size, buf, cap, hash_log)
         assert n > 0
         return buf.raw[:n]
     return model
@@ -113,6 +114,19 @@ def test_gpu_zstd_encode_equals_cpu_model_and_libzstd_decodes_it(capi, oracle, z
     # and back through the GPU decoder
     out, st, _ = capi.decompress_batch(capi.CODEC_ZSTD, comp)
     assert st == [0] * len(parts) and out == parts
+
+
+def test_zstd_level_selects_the_match_finder_table(capi, oracle, zmodel):
+    """spark.io.compression.zstd.level reaches the kernels: 1 -> 2^11-entry hash table, 2 / unspecified -> 2^12,
+    >= 3 -> 2^13; every level's frames equal the CPU model at that table size and are read by libzstd"""
+    p = corpus(oracle, "text", 300000, 5) + corpus(oracle, "terasort", 200000, 6)
+    sizes = {}
+    for level, hlog in ((0, 12), (1, 11), (2, 12), (3, 13), (9, 13)):
+        comp, _, st = capi.compress_batch(capi.CODEC_ZSTD, [p], 32768, level=level)
+        assert st == [0] and zstd_ref.decompress(comp[0]) == p
+        assert comp[0] == zmodel(p, 32768, hlog), level
+        sizes[level] = len(comp[0])
+    assert sizes[3] <= sizes[2] <= sizes[1] and sizes[3] < sizes[1]
 
 
 @pytest.mark.parametrize("bs", [64, 4096, 65536])

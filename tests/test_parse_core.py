@@ -26,6 +26,9 @@ def ph(tmp_path_factory):
     L = C.CDLL(so)
     L.ph_parse.restype = C.c_int
     L.ph_parse.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ph_parse4.restype = C.c_int
+    L.ph_parse4.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_void_p]
     return L
 
 
@@ -85,8 +88,9 @@ def corpora():
     }
 
 
+@pytest.mark.parametrize("variant", [0, 10], ids=["fixed-trip", "event-driven"])
 @pytest.mark.parametrize("name", sorted(corpora().keys()))
-def test_lz4_records_equal_the_specification(ph, name):
+def test_lz4_records_equal_the_specification(ph, name, variant):
     data = corpora()[name]
     for n in (32768, 32767, 20001, 4097, 64, 40, 13, 12, 5, 1, 0):
         blk = data[:n]
@@ -94,7 +98,7 @@ def test_lz4_records_equal_the_specification(ph, name):
             continue
         want = oracle.lz4_compress_block(blk, win=True, cap=max(len(blk) - 1, 0)) if n else None
         for sb in range(4):
-            recs, offs, csize, size = parse(ph, 0, blk, sb)
+            recs, offs, csize, size = parse(ph, variant, blk, sb)
             if want is None:  # does not fit below originalLength: LZ4BlockOutputStream stores RAW
                 assert csize == (n | 0x80000000) and size == 21 + n, (name, n, sb)
                 continue
@@ -103,24 +107,26 @@ def test_lz4_records_equal_the_specification(ph, name):
             assert csize == len(want) and size == 21 + len(want)
 
 
-def test_lz4_64k_blocks_without_the_flag(ph):
+@pytest.mark.parametrize("variant", [0, 10], ids=["fixed-trip", "event-driven"])
+def test_lz4_64k_blocks_without_the_flag(ph, variant):
     """rows longer than 32768 positions cannot spare bit 15: every match goes through the extension"""
     c = corpora()
     data = (c["terasort"] + c["text"] + c["zeros"])[:65536]
     for n in (65536, 50000, 32800):
         blk = data[:n]
         want = oracle.lz4_compress_block(blk, win=True, cap=n - 1)
-        recs, offs, csize, _ = parse(ph, 0, blk, 1)
+        recs, offs, csize, _ = parse(ph, variant, blk, 1)
         assert want is not None and lz4_bytes_from_records(blk, recs, offs) == want and csize == len(want)
 
 
-def test_snappy_and_zstd_variants_agree_on_the_sequences(ph):
+@pytest.mark.parametrize("variant", [0, 10], ids=["fixed-trip", "event-driven"])
+def test_snappy_and_zstd_variants_agree_on_the_sequences(ph, variant):
     c = corpora()
     for name in ("terasort", "text", "zeros", "runs", "random"):
         blk = c[name][:32768]
-        r0, o0, _, _ = parse(ph, 0, blk, 2)
-        r1, o1, cs1, sz1 = parse(ph, 1, blk, 2)
-        r2, o2, _, _ = parse(ph, 2, blk, 2)
+        r0, o0, _, _ = parse(ph, variant + 0, blk, 2)
+        r1, o1, cs1, sz1 = parse(ph, variant + 1, blk, 2)
+        r2, o2, _, _ = parse(ph, variant + 2, blk, 2)
         # the Snappy element stream of the specification has exactly csize bytes (xerial: BE32 length + block)
         x = oracle.xerial_compress(blk, 32768, compressor=1)
         assert len(x) == 16 + 4 + cs1 and sz1 == 4 + cs1, name
@@ -136,3 +142,45 @@ def test_snappy_and_zstd_variants_agree_on_the_sequences(ph):
             assert (y >> 16) == lits
             lits += x_ >> 16
         assert lits + sum(m[1] for m in m2) == len(blk)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# generation 4: sub-chunk parallel parse (walk_subchunk per lane + the kernel's stitch, restated in the harness)
+def parse4(L, codec, data, block_size, sb=0, hash_log=12):
+    a = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(0, dtype=np.uint8)
+    n = a.size
+    rec = np.zeros(3 * (n // 4 + 34) + 8, dtype=np.uint32)
+    nseq, csize, size = C.c_uint32(), C.c_uint32(), C.c_uint64()
+    buf = np.ascontiguousarray(a)
+    rc = L.ph_parse4(codec, buf.ctypes.data if n else None, n, sb, hash_log, block_size, C.byref(nseq), C.byref(csize),
+                     C.byref(size), rec.ctypes.data)
+    assert rc == 0
+    k = nseq.value
+    return rec[: 2 * k].reshape(k, 2), rec[2 * (n // 4 + 34): 2 * (n // 4 + 34) + k], csize.value, size.value
+
+
+@pytest.mark.parametrize("name", sorted(corpora().keys()))
+def test_subchunk_parse_equals_the_specification(ph, name):
+    """32 lanes x walk_subchunk + stitch == orc_lz4_compress_block_win_sub with the kernel's sub-chunk size"""
+    data = corpora()[name]
+    for bs, n in ((32768, 32768), (32768, 32767), (32768, 20001), (32768, 1025), (32768, 1024), (32768, 1023),
+                  (32768, 40), (32768, 13), (32768, 12), (32768, 0), (4096, 4096), (4096, 777), (64, 64), (64, 33),
+                  (65536, 65536), (65536, 40000)):
+        blk = (data * (1 + n // max(len(data), 1)))[:n]
+        sub = oracle.lz4_subchunk(bs)
+        want = oracle.lz4_compress_block(blk, win=True, cap=max(n - 1, 0), sub=sub) if n else None
+        for sb in (0, 3):
+            recs, offs, csize, size = parse4(ph, 0, blk, bs, sb)
+            if want is None:
+                assert csize == (n | 0x80000000) and size == 21 + n, (name, bs, n, sb)
+                continue
+            got = lz4_bytes_from_records(blk, recs, offs)
+            assert got == want, (name, bs, n, sb)
+            assert csize == len(want) and size == 21 + len(want)
+
+
+def test_subchunking_costs_little_ratio():
+    tera = oracle.gen_terasort(11, 3000).tobytes()[:10 * 32768]
+    whole = sum(len(oracle.lz4_compress_block(tera[i:i + 32768], win=True)) for i in range(0, len(tera), 32768))
+    cut = sum(len(oracle.lz4_compress_block(tera[i:i + 32768], win=True, sub=1024)) for i in range(0, len(tera), 32768))
+    assert whole <= cut <= whole * 1.01
