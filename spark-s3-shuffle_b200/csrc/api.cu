@@ -61,6 +61,21 @@ int g_trace = 0;  // B2S_TRACE=1: per-chunk timeline of the compress pipeline on
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int g_read_priority = 1;       // B2S_READ_PRIORITY=0: both lanes at the default stream priority
+int g_read_lag = 2;            // B2S_READ_LAG: chunks between the stages of the read pipeline (upload+sizes | decode | download)
+int g_overlap = 1;             // B2S_OVERLAP=0: match / token kernels on the main stream (no two-stream overlap); A/B runs
+uint64_t g_copy_piece = 0;     // B2S_COPY_PIECE_MB: host<->device payload copies are issued in pieces of this size so the
+                               // copy engines interleave the two lanes' transfers instead of draining one lane's queue
+cudaError_t copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+  if (!g_copy_piece || bytes <= g_copy_piece) return cudaMemcpyAsync(dst, src, bytes, kind, st);
+  for (size_t at = 0; at < bytes; at += g_copy_piece) {
+    const size_t k = std::min<size_t>(g_copy_piece, bytes - at);
+    cudaError_t e = cudaMemcpyAsync((uint8_t*)dst + at, (const uint8_t*)src + at, k, kind, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 // --------------------------------------------------------------------------------------------------------------
 // NUMA placement of pinned staging ("NUMA-pin staging buffers to the GPU's socket").  On the 8-GPU boxes
 // GPUs 0-3 hang off socket 0 and 4-7 off socket 1; pinned arenas that land on the other socket send every H2D/D2H
@@ -421,8 +436,9 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
   // Chunks of `chunk` codec blocks.  The match kernel (issue bound, shared-memory limited) of chunk k+1 runs on the
   // side stream while parse (latency bound, one thread per block), scan and emit of chunk k run on the main stream;
   // the two workspaces alternate.
+  cudaStream_t side = g_overlap ? S.st2 : st;
   CU(cudaEventRecord(S.ev_fork, st));
-  CU(cudaStreamWaitEvent(S.st2, S.ev_fork, 0));
+  CU(cudaStreamWaitEvent(side, S.ev_fork, 0));
   uint32_t k = 0;
   for (uint32_t b0 = 0; b0 < nb; b0 += chunk, k++) {
     const uint32_t m = std::min<uint32_t>(chunk, nb - b0);
@@ -430,10 +446,10 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
     uint8_t* ws = (uint8_t*)S.scratch.p + (size_t)par * ws_bytes;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     S.dom_pair(&e0, &e1);
-    if (k >= 2) CU(cudaStreamWaitEvent(S.st2, S.ev_free[par], 0));  // emit of chunk k-2 has released this workspace
-    launch_lz4_match(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, codec, ws, M.counter + par, S.st2, launches,
+    if (k >= 2) CU(cudaStreamWaitEvent(side, S.ev_free[par], 0));  // emit of chunk k-2 has released this workspace
+    launch_lz4_match(d_src, M.src_off, M.src_len, M.blk_base, n, b0, m, bs, codec, ws, M.counter + par, side, launches,
                      e0, e1, hlog_for_level(codec, level));
-    CU(cudaEventRecord(S.ev_match[par], S.st2));
+    CU(cudaEventRecord(S.ev_match[par], side));
     CU(cudaStreamWaitEvent(st, S.ev_match[par], 0));
     cudaEvent_t t0 = nullptr, t1 = nullptr, tp = nullptr;
     if (g_trace && S.trace.size() < 4096) {
@@ -870,12 +886,14 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
   g_lz4d_tile = env_int("B2S_LZ4D_TILE", g_lz4d_tile);
   g_lz4_pipe = env_int("B2S_LZ4_PIPE", g_lz4_pipe);
   g_lz4d_tokens = env_int("B2S_LZ4D_TOKENS", g_lz4d_tokens);
-  g_lz4_match_depth = env_int("B2S_LZ4_MATCH_DEPTH", g_lz4_match_depth);
-  g_lz4d_copy_group = env_int("B2S_LZ4D_COPYGROUP", g_lz4d_copy_group);
   g_lz4_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4_CHUNK_BLOCKS", (int)g_lz4_chunk_blocks));
   g_lz4d_legacy = env_int("B2S_LZ4D_LEGACY", 0);
   g_trace = env_int("B2S_TRACE", 0);
   g_numa = env_int("B2S_NUMA", 1);
+  g_overlap = env_int("B2S_OVERLAP", g_overlap);
+  g_read_priority = env_int("B2S_READ_PRIORITY", g_read_priority);
+  g_read_lag = std::max(1, env_int("B2S_READ_LAG", g_read_lag));
+  g_copy_piece = (uint64_t)std::max(0, env_int("B2S_COPY_PIECE_MB", 0)) << 20;
   g_lz4d_chunk_blocks = (uint32_t)std::max(1, env_int("B2S_LZ4D_CHUNK_BLOCKS", (int)g_lz4d_chunk_blocks));
   g_host_chunk_bytes = (uint64_t)std::max(1, env_int("B2S_HOST_CHUNK_MB", (int)(g_host_chunk_bytes >> 20))) << 20;
   // streams_per_gpu: pipeline slots (stream pairs + staging) per lane, 0 = default; B2S_SLOTS overrides
@@ -893,8 +911,13 @@ int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_
     for (int l = 0; l < kLanes; l++)
       for (int k = 0; k < g_nslot; k++) {
         Slot& S = D->lane[l].slot[k];
-        CU(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&S.st2, cudaStreamNonBlocking));
+        // the read lane's kernels are short and latency bound (token walks, per-stream header walks, two host round
+        // trips per chunk): they get the higher stream priority so they are not queued behind the write lane's grids
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const int prio = (l == kLaneRead && g_read_priority) ? prio_hi : prio_lo;
+        CU(cudaStreamCreateWithPriority(&S.st, cudaStreamNonBlocking, prio));
+        CU(cudaStreamCreateWithPriority(&S.st2, cudaStreamNonBlocking, prio));
         cudaEvent_t* evs2[] = {&S.ev_fork, &S.ev_match[0], &S.ev_match[1], &S.ev_free[0], &S.ev_free[1]};
         for (auto p : evs2) CU(cudaEventCreateWithFlags(p, cudaEventDisableTiming));
         cudaEvent_t* evs[] = {&S.ev_a, &S.ev_b, &S.ev_k0, &S.ev_k1, &S.ev_t0, &S.ev_t1, &S.ev_h0, &S.ev_h1, &S.ev_d0, &S.ev_d1};
@@ -1172,7 +1195,7 @@ static int checksum_host(uint32_t alg, uint32_t n, const uint8_t* const* ptr, co
     if (rc) return rc;
     CU(cudaEventRecord(S.ev_h0, S.st));
     for (const Run& r : runs)
-      CU(cudaMemcpyAsync((uint8_t*)S.src.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, S.st));
+      CU(copy_async((uint8_t*)S.src.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, S.st));
     CU(cudaEventRecord(S.ev_h1, S.st));
     rc = checksum_chunk_dev(D, S, alg, cnt, (const uint8_t*)S.src.p, dev_off.data(), len + i0, out + i0, bytes,
                             &launches);
@@ -1310,11 +1333,11 @@ static int compress_host(uint32_t codec, int32_t level, uint32_t codec_block_siz
         }
         // copy what fits so that earlier streams of the chunk stay valid
         uint64_t fit = packed_cap > run_off ? packed_cap - run_off : 0;
-        if (fit) CU(cudaMemcpyAsync(packed_dst + run_off, S.dst.p, fit, cudaMemcpyDeviceToHost, S.st));
+        if (fit) CU(copy_async(packed_dst + run_off, S.dst.p, fit, cudaMemcpyDeviceToHost, S.st));
         t_timing.d2h_bytes += fit;
       } else {
         for (uint32_t k = 0; k < J.n; k++) dst_off[i0 + k] = run_off + J.h_dst_off[k];
-        if (chunk_total) CU(cudaMemcpyAsync(packed_dst + run_off, S.dst.p, chunk_total, cudaMemcpyDeviceToHost, S.st));
+        if (chunk_total) CU(copy_async(packed_dst + run_off, S.dst.p, chunk_total, cudaMemcpyDeviceToHost, S.st));
         t_timing.d2h_bytes += chunk_total;
       }
       run_off += chunk_total;
@@ -1358,7 +1381,7 @@ static int compress_host(uint32_t codec, int32_t level, uint32_t codec_block_siz
     if (rc) return rc;
     CU(cudaEventRecord(S.ev_h0, S.st));
     for (const Run& r : runs[c % g_nslot])
-      CU(cudaMemcpyAsync((uint8_t*)S.src.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, S.st));
+      CU(copy_async((uint8_t*)S.src.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, S.st));
     CU(cudaEventRecord(S.ev_h1, S.st));
     t_timing.h2d_bytes += bytes;
     t_timing.src_bytes += bytes;
@@ -1622,7 +1645,7 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
     if (r) return r;
     CU(cudaEventRecord(S.ev_h0, S.st));
     for (const Run& q : runs[c % g_nslot])
-      CU(cudaMemcpyAsync((uint8_t*)S.src.p + q.dev_off, q.host, q.bytes, cudaMemcpyHostToDevice, S.st));
+      CU(copy_async((uint8_t*)S.src.p + q.dev_off, q.host, q.bytes, cudaMemcpyHostToDevice, S.st));
     CU(cudaEventRecord(S.ev_h1, S.st));
     t_timing.h2d_bytes += bytes;
     t_timing.src_bytes += bytes;
@@ -1666,7 +1689,7 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
           if (status[i0 + k] == 0 && run_off + J.h_dst_off[k] + J.h_dst_len[k] > packed_cap)
             status[i0 + k] = B2S_E_DST_TOO_SMALL;
       }
-      if (fit) CU(cudaMemcpyAsync(packed_dst + run_off, S.dst.p, fit, cudaMemcpyDeviceToHost, S.st));
+      if (fit) CU(copy_async(packed_dst + run_off, S.dst.p, fit, cudaMemcpyDeviceToHost, S.st));
       t_timing.d2h_bytes += fit;
     } else {
       for (uint32_t k = 0; k < J.n; k++) {
@@ -1688,10 +1711,14 @@ static int decompress_host(uint32_t codec, uint32_t alg, uint32_t n, const uint8
 
   // software pipeline over the chunks: enqueue chunk c's upload + phase A first (never blocks on younger work), then
   // phase B of chunk c-1 (waits for its sizes), then the download of chunk c-2 (waits for its decode)
-  for (size_t c = 0; c < nchunks + 2; c++) {
+  // (lag chunks between the stages, so that lag uploads / decodes are queued on the device while the host waits for one
+  // chunk's sizes — the write lane keeps g_nslot chunks in flight and would otherwise own the copy queues; needs
+  // 2 * lag + 1 <= g_nslot slots)
+  const size_t lag = (size_t)std::max(1, std::min(g_read_lag, (g_nslot - 1) / 2));
+  for (size_t c = 0; c < nchunks + 2 * lag; c++) {
     if (c < nchunks && (rc = stage_a(c))) return rc;
-    if (c >= 1 && c - 1 < nchunks && (rc = stage_b(c - 1))) return rc;
-    if (c >= 2 && c - 2 < nchunks && (rc = stage_c(c - 2))) return rc;
+    if (c >= lag && c - lag < nchunks && (rc = stage_b(c - lag))) return rc;
+    if (c >= 2 * lag && c - 2 * lag < nchunks && (rc = stage_c(c - 2 * lag))) return rc;
   }
   for (int k = 0; k < g_nslot; k++) {
     CU(cudaStreamSynchronize(Ln.slot[k].st));

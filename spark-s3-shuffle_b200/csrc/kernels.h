@@ -42,7 +42,7 @@ void launch_xxh32_verify(const BlockDesc* d_desc, uint32_t n_blocks, const uint8
                          uint32_t mask, int32_t* d_status, cudaStream_t st, uint64_t* launches);
 
 // ---------------- lz4_compress.cu (K3: match / parse / emit + write-side LZ4Block framing) ----------------
-extern int g_lz4_hlog, g_lz4d_tile, g_lz4_pipe, g_lz4d_tokens, g_lz4_match_depth, g_lz4d_copy_group;
+extern int g_lz4_hlog, g_lz4d_tile, g_lz4_pipe, g_lz4d_tokens;
 // bytes of workspace for one pass over `chunk_blocks` codec blocks (off u16 + ml8 u8 per position, 8-byte records)
 size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size, uint32_t codec);
 // Codec blocks [b0, b0+m) of the batch, in two halves that may run on different streams (d_ws is handed from one to

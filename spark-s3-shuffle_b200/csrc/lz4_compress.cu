@@ -408,29 +408,28 @@ __global__ void __launch_bounds__(64) lz4_parse_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// A2 / B2: the second generation of the match and parse kernels (same specification, same bytes out)
+// A2 / B4: the alternative generation (B2S_LZ4_PIPE=4): match without lengths, sub-chunk parallel parse
 // ------------------------------------------------------------------------------------------------------------
 // ncu of the first generation (profiles/r1z_final.md): the match kernel is issue bound at 152 warp-instructions per
 // window, and about half of them compute FULL match lengths for all 32 positions (8-byte compares = a third candidate
 // word and a third source word per lane, segment ballots, the cooperative extension loop, the carry) although the
-// greedy parse consults only ~4 positions per window.  Second generation:
+// greedy parse consults only ~4 positions per window.
 //
-//   A2 lz4_match2_kernel  verifies FOUR bytes and stores off[p] only (2 B per position instead of 4).  The candidate
-//                         and source word pairs already hold the fifth byte, so for codec blocks <= 32 KiB (offsets
-//                         < 2^15) bit 15 of off[p] says "the match is exactly 4 long" — the common case on
-//                         record-shaped data (12 of 14 sequences per terasort record).
-//   B2 lz4_parse2_kernel  still one THREAD per block and a fixed-trip loop, now over groups of FOUR positions (a match
-//                         is >= 4 long: at most one sequence starts per group and its extension starts in the next
-//                         group).  A lane whose match is not flagged "exactly 4" extends it on the source itself, four
-//                         bytes per group, while it walks over the groups the match covers; the candidate words of
-//                         the next group are requested one iteration ahead.  Source and off[] stream through a
-//                         register ring (next trip's loads are issued at the top of the current trip).
+//   A2 lz4_match2_kernel  verifies FOUR bytes and stores off[p] only (2 B per position instead of 4) + one 32-bit
+//                         match mask per window.  The candidate and source word pairs already hold the fifth byte, so
+//                         for codec blocks <= 32 KiB (offsets < 2^15) bit 15 of off[p] says "the match is exactly 4
+//                         long" — the common case on record-shaped data (12 of 14 sequences per terasort record).
+//                         71 (81 with the masks) instead of 152 warp-instructions per window, DRAM traffic 2.2x instead
+//                         of 3.7x algorithmic (profiles/r2_compress_generations.md).
+//   B4 lz4_parse4_kernel  one WARP per block, lane per sub-chunk, lengths measured for the matches the parse takes.
+// Measured end to end this generation is NOT faster than the first (what the match kernel saves, measuring lengths per
+// taken match costs again in scattered 32-byte-sector traffic) — it is kept for its lower latency on task-sized batches.
 struct Pending2 {
   uint32_t c0, c1, v, b4, d;  // candidate words, the 4 source bytes, source word holding byte p+4 (pre-shifted), offset (0 = dead)
   unsigned csh;
 };
 
-template <int HLOG, int DEPTH>
+template <int HLOG>
 __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
     const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
     const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
@@ -529,39 +528,10 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
       }
     };
 
-    Pending2 PA, PB, PC;
+    Pending2 PA, PB;
     PA.c0 = PA.c1 = PA.v = PA.b4 = PA.d = 0;
     PA.csh = 0;
     PB = PA;
-    PC = PA;
-    if (DEPTH == 2) {
-      // candidate words requested TWO windows ahead of their use (three pending windows rotate): ncu of the one-ahead
-      // loop shows the kernel waiting on them (long_scoreboard 6 warps per issue, issue slots 54 % busy)
-      int k = 0;
-      for (int pos = 0; pos <= mflimit; pos += 96) {
-        step(pos, PA, PB, pos > 0);  // finishes the window requested two steps ago
-        k = 1;
-        if (pos + 32 > mflimit) break;
-        step(pos + 32, PB, PC, pos > 0);
-        k = 2;
-        if (pos + 64 > mflimit) break;
-        step(pos + 64, PC, PA, true);
-        k = 3;
-      }
-      // two windows are still pending, oldest first
-      if (k == 1) {
-        if (mflimit >= 32) finish(PC);
-        finish(PA);
-      } else if (k == 2) {
-        finish(PA);
-        finish(PB);
-      } else {
-        finish(PB);
-        finish(PC);
-      }
-      __syncwarp();
-      continue;
-    }
     bool last_is_a = true;
     for (int pos = 0; pos <= mflimit; pos += 64) {
       step(pos, PA, PB, pos > 0);
@@ -575,46 +545,10 @@ __global__ void __launch_bounds__(kMatchWarps * 32, 3) lz4_match2_kernel(
   }
 }
 
-// B2: thread per block around parse_block() of lz4_parse_core.h (host/device; unit-tested on the CPU against the oracle)
 struct ParseMemDev {
-  const uint4* __restrict__ ov;    // the block's off[] row, 8 positions per vector
-  const uint32_t* __restrict__ wp; // aligned word stream holding the block's bytes
-  const uint32_t* __restrict__ mk; // the block's window masks (event-driven variant)
-  int ovmax, kmax;
+  const uint32_t* __restrict__ mk;  // the block's window masks
   __device__ __forceinline__ uint32_t mask(int w) const { return __ldg(mk + w); }
-  __device__ __forceinline__ uint32_t off16(int q) const { return __ldg(reinterpret_cast<const uint16_t*>(ov) + q); }
-  __device__ __forceinline__ uint4 off8(int i) const { return __ldcs(ov + (i < ovmax ? i : ovmax)); }
-  __device__ __forceinline__ uint32_t word(int k) const { return __ldg(wp + (k < kmax ? k : kmax)); }
-  __device__ __forceinline__ uint32_t cand_word(int k) const { return __ldg(wp + k); }
 };
-
-template <int CODEC, bool EV>
-__global__ void __launch_bounds__(64) lz4_parse2_kernel(
-    const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ src_len,
-    const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
-    uint32_t stride, uint32_t max_seq, const uint16_t* __restrict__ offarr, const uint32_t* __restrict__ maskarr,
-    uint2* __restrict__ seqarr, uint32_t* __restrict__ nseq, uint32_t* __restrict__ csize,
-    uint64_t* __restrict__ sizes) {
-  const uint32_t bl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (bl >= m) return;
-  const uint32_t b = b0 + bl;
-  const BlockSpan B = block_span(src_base, src_off, src_len, blk_base, n_streams, b, block_size);
-  const uintptr_t a0 = reinterpret_cast<uintptr_t>(B.s);
-  const int sb = (int)(a0 & 3u);
-  ParseMemDev mem;
-  mem.ov = reinterpret_cast<const uint4*>(offarr + (size_t)bl * stride);
-  mem.wp = reinterpret_cast<const uint32_t*>(a0 & ~uintptr_t(3));
-  mem.mk = maskarr + (size_t)bl * (stride >> 5);
-  mem.ovmax = (int)(stride >> 3) - 1;
-  mem.kmax = B.n > 0 ? (sb + B.n - 1) >> 2 : 0;
-  const lzparse::Result r = EV ? lzparse::parse_block_ev<CODEC>(mem, B.n, sb, stride, seqarr + (size_t)bl * max_seq)
-                               : lzparse::parse_block<CODEC>(mem, B.n, sb, stride, seqarr + (size_t)bl * max_seq);
-  nseq[b] = r.nseq;
-  if (CODEC != 2) {
-    csize[b] = r.csize;
-    sizes[b] = r.size;
-  }
-}
 
 // B4: sub-chunk parallel parse — one WARP per codec block, lane k parses sub-chunk k (lz4_parse_core.h, walk_subchunk),
 // then the warp stitches the 32 staged record lists into the dense record array the emit kernels read:
@@ -646,14 +580,8 @@ __global__ void __launch_bounds__(kParse4Warps * 32) lz4_parse4_kernel(
   const int S = (int)parse4_sub(stride);
   const int slot = S / 4 + 1;
   uint2* seq = seqarr + (size_t)bl * max_seq;
-  const uintptr_t a0 = reinterpret_cast<uintptr_t>(B.s);
-  const int sb = (int)(a0 & 3u);
   ParseMemDev mem;
-  mem.ov = reinterpret_cast<const uint4*>(offarr + (size_t)bl * stride);
-  mem.wp = reinterpret_cast<const uint32_t*>(a0 & ~uintptr_t(3));
   mem.mk = maskarr + (size_t)bl * (stride >> 5);
-  mem.ovmax = (int)(stride >> 3) - 1;
-  mem.kmax = n > 0 ? (sb + n - 1) >> 2 : 0;
 
   const int lo = lane * S;
   lzparse::SubResult R;
@@ -661,9 +589,96 @@ __global__ void __launch_bounds__(kParse4Warps * 32) lz4_parse4_kernel(
   R.rest = 0;
   R.pm0 = R.len0 = R.d0 = 0;
   R.last_end = -1;
-  if (n >= kMFLimit + 1 && lo < n) {
+  if (n >= kMFLimit + 1) {
+    // The walk of lzparse::walk_subchunk (the lane-local statement of this loop, tested on the CPU), restructured so
+    // that the 32 lanes advance one SEQUENCE per trip in lock step and matches that need measuring are measured by the
+    // whole warp: 32 consecutive bytes of the match against 32 consecutive bytes of its source per round — two
+    // coalesced loads instead of a per-lane gather of six words per eight bytes (ncu of the per-lane version: 11.5 GB
+    // of DRAM reads per GiB of input, 80 bytes per sequence, almost all of it extension traffic).
+    const uint8_t* __restrict__ s = B.s;
+    const bool flag4 = stride <= 32768u;
+    const uint32_t omask = flag4 ? 0x7fffu : 0xffffu;
+    const int mflimit = n - kMFLimit, matchlimit = n - kLastLiterals;
     const int hi = lo + S < n ? lo + S : n;
-    R = lzparse::walk_subchunk<CODEC>(mem, n, sb, stride, lo, hi, seq + (size_t)lane * slot);
+    const int plim = mflimit < hi - 4 ? mflimit : hi - 4;
+    const int elim = matchlimit < hi ? matchlimit : hi;
+    const int last_w = plim >> 5;
+    const uint16_t* __restrict__ offrow = offarr + (size_t)bl * stride;
+    bool done = lo >= n || lo > plim;
+    int wi = lo >> 5;
+    uint32_t mw = done ? 0u : mem.mask(wi);
+    int anchor = lo, rel = 0;
+    uint2* sp = seq + (size_t)lane * slot;
+    uint2* const sp0 = sp;
+    while (!__all_sync(FULL, done)) {
+      // A: next match at or after my cursor
+      int pm = -1, ed = 0, len = 4;
+      bool x4 = true;
+      while (!done && pm < 0) {
+        if (mw == 0u) {
+          wi++;
+          if (wi > last_w) done = true;
+          else mw = mem.mask(wi);
+        } else {
+          const int q = (wi << 5) + __ffs(mw) - 1;
+          if (q > plim) {
+            done = true;
+          } else {
+            pm = q;
+            const uint32_t o16 = offrow[q];
+            ed = (int)(o16 & omask);
+            x4 = (flag4 && (o16 & 0x8000u)) || q + 4 >= elim;
+          }
+        }
+      }
+      // B: measure the matches that are not flagged "exactly 4", one after the other, with all lanes
+      unsigned need = __ballot_sync(FULL, pm >= 0 && !x4);
+      while (need) {
+        const int l = __ffs(need) - 1;
+        need &= need - 1;
+        const int pm_l = __shfl_sync(FULL, pm, l), d_l = __shfl_sync(FULL, ed, l), elim_l = __shfl_sync(FULL, elim, l);
+        int len_l = elim_l - pm_l;
+        for (int pos = pm_l + 4 + lane;; pos += 32) {
+          const bool stop = pos >= elim_l || __ldg(s + pos) != __ldg(s + pos - d_l);
+          const unsigned bm = __ballot_sync(FULL, stop);
+          if (bm) {
+            const int e = pos - lane + __ffs(bm) - 1;
+            len_l = (e < elim_l ? e : elim_l) - pm_l;
+            break;
+          }
+        }
+        if (lane == l) len = len_l;
+      }
+      // C: one sequence per lane
+      if (pm >= 0) {
+        if (sp == sp0) {
+          R.pm0 = pm;
+          R.len0 = len;
+          R.d0 = ed;
+          *sp++ = make_uint2((uint32_t)pm, (uint32_t)len);
+        } else {
+          const int lit = pm - anchor;
+          *sp++ = make_uint2((uint32_t)anchor | ((uint32_t)lit << 16), (uint32_t)len | ((uint32_t)rel << 16));
+          rel += lzparse::seq_size<CODEC>(lit, len, ed);
+        }
+        const int p = pm + len;
+        anchor = p;
+        const int nw = p >> 5;
+        if (nw != wi) {
+          wi = nw;
+          if (wi > last_w) {
+            done = true;
+            mw = 0u;
+          } else {
+            mw = mem.mask(wi);
+          }
+        }
+        mw &= ~0u << (p & 31);
+      }
+    }
+    R.nrec = (int)(sp - sp0);
+    R.rest = rel;
+    R.last_end = R.nrec ? anchor : -1;
   }
   __syncwarp();  // staged records are visible to the other lanes
 
@@ -880,12 +895,19 @@ __global__ void __launch_bounds__(kEmitThreads) lz4_emit_kernel(
 // launchers
 // ------------------------------------------------------------------------------------------------------------
 int g_lz4_hlog = 12;  // B2S_LZ4_HLOG (api.cu reads it once at init); 12 is the specified default
-int g_lz4_match_depth = 1;  // B2S_LZ4_MATCH_DEPTH: windows between requesting and using the candidate words (1 or 2)
-// B2S_LZ4_PIPE: 4 = match2 + sub-chunk parallel parse (LZ4Block; Snappy and Zstandard stay on generation 1: their CPU
-// models state the single-cursor parse); 1 = first generation; 2 / 3 = match2 + thread-per-block parse with in-parse
-// extension (fixed-trip / event-driven) — measured slower, kept for A/B runs (profiles/r2a_*, r2c_*)
-int g_lz4_pipe = 4;
-static int pipe_for(uint32_t codec) { return g_lz4_pipe == 4 && codec != B2S_CODEC_LZ4BLOCK ? 1 : g_lz4_pipe; }
+// B2S_LZ4_PIPE selects the match / parse generation (read once at b2s_init):
+//   1 (default)  lz4_match_kernel (offsets + full match lengths) -> lz4_parse_kernel (thread per block, no source access)
+//   4            lz4_match2_kernel (offsets only, 71 instead of 152 warp-instructions per window) -> lz4_parse4_kernel
+//                (warp per block, lane per sub-chunk).  A different — sub-chunked — parse, i.e. slightly different
+//                bytes (specification: compressor 2 in oracle/); lower latency for task-sized batches, but measured
+//                slower at scale: what the match kernel saves, measuring matches lane by lane costs again in scattered
+//                32-byte-sector traffic (profiles/r2_compress_generations.md)
+//   (2 / 3, match2 -> thread-per-block parses with in-parse extension, were measured slower still and removed)
+int g_lz4_pipe = 1;
+static int pipe_for(uint32_t codec) {
+  (void)codec;
+  return g_lz4_pipe;
+}
 
 template <int HLOG>
 static void launch_match_t(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
@@ -911,15 +933,14 @@ static void launch_match2_t(const uint8_t* src_base, const uint64_t* d_src_off, 
                             uint32_t block_size, uint32_t stride, uint16_t* d_off, uint32_t* d_mask,
                             unsigned int* d_counter, cudaStream_t st) {
   const size_t smem = (size_t)kMatchWarps * (2u << HLOG);
-  auto kern = g_lz4_match_depth == 2 ? lz4_match2_kernel<HLOG, 2> : lz4_match2_kernel<HLOG, 1>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(lz4_match2_kernel<HLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMatchWarps * 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_match2_kernel<HLOG>, kMatchWarps * 32, smem);
   if (per_sm < 1) per_sm = 1;
   uint64_t want = ((uint64_t)m + kMatchWarps - 1) / kMatchWarps;
   uint64_t grid = (uint64_t)kSMs * per_sm;  // persistent: one wave, warps pull blocks from the counter
   if (grid > want) grid = want;
-  kern<<<(unsigned)grid, kMatchWarps * 32, smem, st>>>(
+  lz4_match2_kernel<HLOG><<<(unsigned)grid, kMatchWarps * 32, smem, st>>>(
       src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, d_off, d_mask, d_counter);
 }
 
@@ -975,17 +996,9 @@ static void launch_parse_t(const uint8_t* src_base, const uint64_t* d_src_off, c
     lz4_parse4_kernel<CODEC><<<(m + kParse4Warps - 1) / kParse4Warps, kParse4Warps * 32, 0, st>>>(
         src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq, w.off, w.mask,
         w.seq, d_nseq, d_csize, d_sizes);
-  else if (pipe == 1)
+  else
     lz4_parse_kernel<CODEC><<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride,
                                                           w.max_seq, w.ml, w.seq, d_nseq, d_csize, d_sizes);
-  else if (pipe == 2)
-    lz4_parse2_kernel<CODEC, false><<<(m + 63) / 64, 64, 0, st>>>(
-        src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq, w.off,
-        w.mask, w.seq, d_nseq, d_csize, d_sizes);
-  else
-    lz4_parse2_kernel<CODEC, true><<<(m + 63) / 64, 64, 0, st>>>(
-        src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, w.stride, w.max_seq, w.off,
-        w.mask, w.seq, d_nseq, d_csize, d_sizes);
 }
 
 void launch_lz4_match(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,

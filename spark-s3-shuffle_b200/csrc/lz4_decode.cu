@@ -22,7 +22,6 @@
 namespace b2s {
 
 constexpr int kMinMatch = 4, kMFLimit = 12, kLastLiterals = 5;
-int g_lz4d_copy_group = 1;  // B2S_LZ4D_COPYGROUP: bytes of a short match per trip in the copy kernel (1 or 4)
 int g_lz4d_tokens = 1;  // B2S_LZ4D_TOKENS: 1 = global loads + L1 prefetch, 2 = TMA ring (tma_ring.cuh)
 
 // record: x = literal count | match length << 16 (0 = final sequence) ; y = offset | literal source position << 16
@@ -263,7 +262,6 @@ __global__ void __launch_bounds__(kTokThreads) lz4_tokens_tma_kernel(const Block
 }
 
 constexpr int kCopyThreads = 256;
-template <int GROUP>
 __global__ void __launch_bounds__(kCopyThreads) lz4_copy_kernel(const BlockDesc* __restrict__ desc, uint32_t b0,
                                                                 uint32_t m, const uint8_t* __restrict__ src_base,
                                                                 uint8_t* dst_base, const uint2* __restrict__ rec,
@@ -317,7 +315,7 @@ __global__ void __launch_bounds__(kCopyThreads) lz4_copy_kernel(const BlockDesc*
     __syncwarp();
 
     // ---- matches, in dependency rounds (lz_batch.cuh)
-    lz_execute_matches<GROUP>(out, op + lit, ml, off, lane);
+    lz_execute_matches(out, op + lit, ml, off, lane);
   }
 }
 
@@ -354,12 +352,8 @@ void launch_lz4_copy(const BlockDesc* d_desc, uint32_t b0, uint32_t m, uint32_t 
                      uint8_t* dst_base, const uint8_t* d_ws, const uint32_t* d_nrec, cudaStream_t st,
                      uint64_t* launches) {
   if (!m) return;
-  if (g_lz4d_copy_group == 4)
-    lz4_copy_kernel<4><<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
-        d_desc, b0, m, src_base, dst_base, reinterpret_cast<const uint2*>(d_ws), rec_stride, d_nrec);
-  else
-    lz4_copy_kernel<1><<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
-        d_desc, b0, m, src_base, dst_base, reinterpret_cast<const uint2*>(d_ws), rec_stride, d_nrec);
+  lz4_copy_kernel<<<(m + kCopyThreads / 32 - 1) / (kCopyThreads / 32), kCopyThreads, 0, st>>>(
+      d_desc, b0, m, src_base, dst_base, reinterpret_cast<const uint2*>(d_ws), rec_stride, d_nrec);
   *launches += 1;
 }
 

@@ -16,11 +16,8 @@
 
 namespace b2s {
 
-// GROUP: bytes of a short match moved per trip.  1 = byte by byte: the load of byte j+1 is issued only after the store of
-// byte j (in-order issue), i.e. one memory round trip per byte of the match.  4 = groups of four when the group's
-// source cannot be its own output (off >= 4 or the whole match is disjoint): four independent loads, then four stores —
-// a quarter of the round trips on the dependency chain that bounds the copy kernel.
-template <int GROUP = 1>
+// (Tried: moving a short match in groups of four bytes — four independent loads, then four stores — when the group's
+// source cannot be its own output: the read pass got slower, 60.5 vs 57.8 ms per 10 GiB, profiles/r2_decode_variants.md.)
 __device__ __forceinline__ void lz_execute_matches(uint8_t* out, int mdst, int ml, int off, int lane) {
   constexpr unsigned FULL = 0xffffffffu;
   const int msrc = mdst - off;
@@ -47,20 +44,8 @@ __device__ __forceinline__ void lz_execute_matches(uint8_t* out, int mdst, int m
   while (done != FULL) {
     const bool ready = pending && (need & ~done) == 0;
     if (ready && ml <= 16) {
-      if (GROUP == 4 && (off >= 4 || off >= ml)) {
-        for (int g = 0; g < ml; g += 4) {
-          const int k = ml - g;  // >= 1 bytes left
-          const uint8_t b0 = out[msrc + g], b1 = k > 1 ? out[msrc + g + 1] : (uint8_t)0,
-                        b2 = k > 2 ? out[msrc + g + 2] : (uint8_t)0, b3 = k > 3 ? out[msrc + g + 3] : (uint8_t)0;
-          out[mdst + g] = b0;
-          if (k > 1) out[mdst + g + 1] = b1;
-          if (k > 2) out[mdst + g + 2] = b2;
-          if (k > 3) out[mdst + g + 3] = b3;
-        }
-      } else {
-        // sequential byte copy: also right for an overlapping match (off < ml)
-        for (int j = 0; j < ml; j++) out[mdst + j] = out[msrc + j];
-      }
+      // sequential byte copy: also right for an overlapping match (off < ml)
+      for (int j = 0; j < ml; j++) out[mdst + j] = out[msrc + j];
     }
     unsigned longmask = __ballot_sync(FULL, ready && ml > 16);
     while (longmask) {

@@ -1,6 +1,7 @@
-// Host build of spark-s3-shuffle_b200/csrc/lz4_parse_core.h for tests/test_parse_core.py: the very function
-// lz4_parse2_kernel runs per thread, compiled by g++ so the greedy parse + in-parse extension can be checked against
-// the oracle (orc_lz4_compress_block_win / orc_snappy_compress_raw_win) without a GPU.
+// Host build of spark-s3-shuffle_b200/csrc/lz4_parse_core.h for tests/test_parse_core.py: the lane-local walk of the
+// sub-chunk parallel parse (B2S_LZ4_PIPE=4) compiled by g++, run for the 32 lanes of a warp and stitched like
+// lz4_parse4_kernel does, so the result can be checked against the oracle (orc_lz4_compress_block_win_sub /
+// orc_snappy_compress_raw_win_sub) without a GPU.
 // Test infrastructure only — the C ABI never runs this.
 //
 // The off[] input is produced here by a plain restatement of what lz4_match2_kernel writes (the oracle's
@@ -49,11 +50,6 @@ struct MemHost {
   const uint16_t* off;
   const uint8_t* aligned;  // 4-byte aligned start of the word stream
   int ovmax, kmax;
-  uint4 off8(int i) const {
-    uint4 r;
-    memcpy(&r, off + 8 * (size_t)(i < ovmax ? i : ovmax), 16);
-    return r;
-  }
   uint32_t word(int k) const {
     uint32_t r;
     memcpy(&r, aligned + 4 * (size_t)(k < kmax ? k : kmax), 4);
@@ -68,49 +64,6 @@ struct MemHost {
 };
 
 }  // namespace
-
-extern "C" {
-
-// parses `n` bytes placed at byte phase `sb` (0..3) of an aligned buffer; returns the result fields and the records
-int ph_parse(int codec, const unsigned char* src, int n, int sb, int hash_log, unsigned int* nseq, unsigned int* csize,
-             unsigned long long* size, unsigned int* records /* 2 x (n/4+2) */) {
-  const uint32_t stride = ((uint32_t)n + 31u) & ~31u;
-  std::vector<uint32_t> store((size_t)n / 4 + 4, 0xA5A5A5A5u);
-  uint8_t* base = reinterpret_cast<uint8_t*>(store.data());
-  memcpy(base + sb, src, (size_t)n);
-  std::vector<uint16_t> off(stride ? stride : 32);
-  std::vector<uint32_t> mask((stride ? stride : 32) / 32);
-  match_model(base + sb, n, hash_log, stride ? stride : 32, off.data(), mask.data());
-  MemHost mem{mask.data(), off.data(), base, (int)((stride ? stride : 32) >> 3) - 1, n > 0 ? (sb + n - 1) >> 2 : 0};
-  std::vector<uint2> seq((size_t)stride / 4 + 2);
-  b2s::lzparse::Result r;
-  const bool ev = codec >= 10;  // 10..12: the event-driven variant
-  codec %= 10;
-  if (ev) {
-    if (codec == 0) r = b2s::lzparse::parse_block_ev<0>(mem, n, sb, stride, seq.data());
-    else if (codec == 1) r = b2s::lzparse::parse_block_ev<1>(mem, n, sb, stride, seq.data());
-    else r = b2s::lzparse::parse_block_ev<2>(mem, n, sb, stride, seq.data());
-  } else {
-    if (codec == 0) r = b2s::lzparse::parse_block<0>(mem, n, sb, stride, seq.data());
-    else if (codec == 1) r = b2s::lzparse::parse_block<1>(mem, n, sb, stride, seq.data());
-    else r = b2s::lzparse::parse_block<2>(mem, n, sb, stride, seq.data());
-  }
-  *nseq = r.nseq;
-  *csize = r.csize;
-  *size = r.size;
-  for (uint32_t i = 0; i < r.nseq; i++) {
-    records[2 * i] = seq[i].x;
-    records[2 * i + 1] = seq[i].y;
-  }
-  // the offsets the emit kernels would look up (bit 15 masked as they do)
-  const uint32_t omask = stride <= 32768u ? 0x7fffu : 0xffffu;
-  for (uint32_t i = 0; i < r.nseq; i++) {
-    const uint32_t anchor = seq[i].x & 0xffffu, lit = seq[i].x >> 16, ml = seq[i].y & 0xffffu;
-    records[2 * (size_t)(n / 4 + 2) + i] = ml ? (off[anchor + lit] & omask) : 0;
-  }
-  return 0;
-}
-}
 
 // Generation 4: walk_subchunk() for the 32 lanes of a warp, then the kernel's stitch (lz4_parse4_kernel steps 1-4)
 // restated with plain loops.  stride / S exactly as the kernel derives them from the codec block size.

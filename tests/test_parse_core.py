@@ -1,9 +1,11 @@
-"""CPU check of spark-s3-shuffle_b200/csrc/lz4_parse_core.h — the per-thread body of lz4_parse2_kernel — against the
-oracle's executable specification (orc_lz4_compress_block_win, orc_snappy_compress_raw_win via xerial framing).
+"""CPU check of spark-s3-shuffle_b200/csrc/lz4_parse_core.h — the lane-local walk of the sub-chunk parallel parse
+(B2S_LZ4_PIPE=4) — against the oracle's executable specification of that generation (orc_lz4_compress_block_win_sub,
+orc_snappy_compress_raw_win_sub via xerial framing, compressor=2).
 
 The header is compiled by g++ into tests/native/lz4_parse_host.cpp together with a plain restatement of what the match
-kernel hands it (off[] + the "exactly 4" flag); the records are turned into LZ4 block bytes here and must equal the
-oracle's bytes.  No GPU involved; the GPU suite then demands the same bytes from the kernels themselves.
+kernel hands it (off[] + the "exactly 4" flag + the window masks) and of the kernel's stitch; the records are turned into
+LZ4 block bytes here and must equal the oracle's bytes.  No GPU involved; tests/test_gpu_pipe4.py then demands the same
+bytes from the kernels themselves.
 """
 import ctypes as C
 import os
@@ -24,27 +26,10 @@ def ph(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("parse_core") / "libparse_host.so")
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Werror", "-o", so, SRC])
     L = C.CDLL(so)
-    L.ph_parse.restype = C.c_int
-    L.ph_parse.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ph_parse4.restype = C.c_int
     L.ph_parse4.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_void_p]
     return L
-
-
-def parse(L, codec, data, sb=0, hash_log=12):
-    a = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(0, dtype=np.uint8)
-    n = a.size
-    rec = np.zeros(3 * (n // 4 + 2) + 8, dtype=np.uint32)
-    nseq, csize, size = C.c_uint32(), C.c_uint32(), C.c_uint64()
-    buf = np.ascontiguousarray(a)
-    rc = L.ph_parse(codec, buf.ctypes.data if n else None, n, sb, hash_log, C.byref(nseq), C.byref(csize), C.byref(size),
-                    rec.ctypes.data)
-    assert rc == 0
-    k = nseq.value
-    recs = rec[: 2 * k].reshape(k, 2)
-    offs = rec[2 * (n // 4 + 2): 2 * (n // 4 + 2) + k]
-    return recs, offs, csize.value, size.value
 
 
 def lz4_bytes_from_records(data, recs, offs):
@@ -88,62 +73,6 @@ def corpora():
     }
 
 
-@pytest.mark.parametrize("variant", [0, 10], ids=["fixed-trip", "event-driven"])
-@pytest.mark.parametrize("name", sorted(corpora().keys()))
-def test_lz4_records_equal_the_specification(ph, name, variant):
-    data = corpora()[name]
-    for n in (32768, 32767, 20001, 4097, 64, 40, 13, 12, 5, 1, 0):
-        blk = data[:n]
-        if len(blk) < n:
-            continue
-        want = oracle.lz4_compress_block(blk, win=True, cap=max(len(blk) - 1, 0)) if n else None
-        for sb in range(4):
-            recs, offs, csize, size = parse(ph, variant, blk, sb)
-            if want is None:  # does not fit below originalLength: LZ4BlockOutputStream stores RAW
-                assert csize == (n | 0x80000000) and size == 21 + n, (name, n, sb)
-                continue
-            got = lz4_bytes_from_records(blk, recs, offs)
-            assert got == want, (name, n, sb)
-            assert csize == len(want) and size == 21 + len(want)
-
-
-@pytest.mark.parametrize("variant", [0, 10], ids=["fixed-trip", "event-driven"])
-def test_lz4_64k_blocks_without_the_flag(ph, variant):
-    """rows longer than 32768 positions cannot spare bit 15: every match goes through the extension"""
-    c = corpora()
-    data = (c["terasort"] + c["text"] + c["zeros"])[:65536]
-    for n in (65536, 50000, 32800):
-        blk = data[:n]
-        want = oracle.lz4_compress_block(blk, win=True, cap=n - 1)
-        recs, offs, csize, _ = parse(ph, variant, blk, 1)
-        assert want is not None and lz4_bytes_from_records(blk, recs, offs) == want and csize == len(want)
-
-
-@pytest.mark.parametrize("variant", [0, 10], ids=["fixed-trip", "event-driven"])
-def test_snappy_and_zstd_variants_agree_on_the_sequences(ph, variant):
-    c = corpora()
-    for name in ("terasort", "text", "zeros", "runs", "random"):
-        blk = c[name][:32768]
-        r0, o0, _, _ = parse(ph, variant + 0, blk, 2)
-        r1, o1, cs1, sz1 = parse(ph, variant + 1, blk, 2)
-        r2, o2, _, _ = parse(ph, variant + 2, blk, 2)
-        # the Snappy element stream of the specification has exactly csize bytes (xerial: BE32 length + block)
-        x = oracle.xerial_compress(blk, 32768, compressor=1)
-        assert len(x) == 16 + 4 + cs1 and sz1 == 4 + cs1, name
-        # same matches in all three grammars (LZ4 may stop early only when it falls back to RAW, which these do not)
-        m0 = [(int(x_ & 0xFFFF) + int(x_ >> 16), int(y & 0xFFFF), int(o)) for (x_, y), o in zip(r0.tolist(), o0.tolist()) if y & 0xFFFF]
-        m1 = [(int(x_ & 0xFFFF) + int(x_ >> 16), int(y & 0xFFFF), int(o)) for (x_, y), o in zip(r1.tolist(), o1.tolist()) if y & 0xFFFF]
-        m2 = [(int(x_ & 0xFFFF) + int(x_ >> 16), int(y & 0xFFFF), int(o)) for (x_, y), o in zip(r2.tolist(), o2.tolist()) if y & 0xFFFF]
-        if name != "random":
-            assert m0 == m1 == m2, name
-        # Zstandard records carry the running literal count and end with the trailing-literals record
-        lits = 0
-        for x_, y in r2.tolist():
-            assert (y >> 16) == lits
-            lits += x_ >> 16
-        assert lits + sum(m[1] for m in m2) == len(blk)
-
-
 # ------------------------------------------------------------------------------------------------------------------
 # generation 4: sub-chunk parallel parse (walk_subchunk per lane + the kernel's stitch, restated in the harness)
 def parse4(L, codec, data, block_size, sb=0, hash_log=12):
@@ -184,3 +113,25 @@ def test_subchunking_costs_little_ratio():
     whole = sum(len(oracle.lz4_compress_block(tera[i:i + 32768], win=True)) for i in range(0, len(tera), 32768))
     cut = sum(len(oracle.lz4_compress_block(tera[i:i + 32768], win=True, sub=1024)) for i in range(0, len(tera), 32768))
     assert whole <= cut <= whole * 1.01
+
+
+def test_subchunk_parse_snappy_and_zstd_grammars(ph):
+    """generation 4 with the Snappy / Zstandard size rules: the Snappy element stream of the specification
+    (xerial_compress(compressor=2): BE32 length + raw block per chunk) has exactly csize bytes, and all three grammars
+    select the same matches"""
+    c = corpora()
+    for name in ("terasort", "text", "zeros", "runs", "rows"):
+        blk = c[name][:32768]
+        r0, o0, _, _ = parse4(ph, 0, blk, 32768, 1)
+        r1, o1, cs1, sz1 = parse4(ph, 1, blk, 32768, 1)
+        r2, o2, _, _ = parse4(ph, 2, blk, 32768, 1)
+        x = oracle.xerial_compress(blk, 32768, compressor=2)
+        assert len(x) == 16 + 4 + cs1 and sz1 == 4 + cs1, name
+        ms = [[(int(x_ & 0xFFFF) + int(x_ >> 16), int(y & 0xFFFF), int(o)) for (x_, y), o in zip(r.tolist(), o.tolist())
+               if y & 0xFFFF] for r, o in ((r0, o0), (r1, o1), (r2, o2))]
+        assert ms[0] == ms[1] == ms[2], name
+        lits = 0
+        for x_, y in r2.tolist():
+            assert (y >> 16) == lits
+            lits += x_ >> 16
+        assert lits + sum(m[1] for m in ms[2]) == len(blk)

@@ -26,7 +26,7 @@ def main():
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     total = int(os.environ.get("B2S_SWEEP_MIB", "1024")) << 20  # per point (SURVEY asks 4 GiB; 1 GiB keeps the run short)
     rows = []
-    for size in (4 << 10, 16 << 10, 64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20):
+    for size in (4 << 10, 16 << 10, 64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20):
         n = total // size
         recs = (size + 103) // 104
         base = oracle.gen_terasort(0, recs * min(n, 64)).tobytes()
@@ -39,7 +39,7 @@ def main():
         cap = int(c.compress_bound(c.CODEC_ZSTD, 32768, size)) * n
         d_cmp, d_out = c.dev_alloc(cap), c.dev_alloc(src.size)
         for _ in range(2):
-            w = c.compress_dev(c.CODEC_ZSTD, d_src, off, ln, d_cmp, cap, 32768)
+            w = c.compress_dev(c.CODEC_ZSTD, d_src, off, ln, d_cmp, cap, 32768, level=3)
         tw = c.last_timing()["kernel_ms"]
         # read leg on libzstd level-3 frames
         frames = [zstd_ref.compress_stream(p, level=3) for p in parts[:64]]
@@ -54,17 +54,27 @@ def main():
         tr = c.last_timing()["kernel_ms"]
         assert not w["status"].any() and not r["status"].any() and r["total"] == src.size
         rg, rl = w["total"] / src.size, fsrc.size / src.size
-        rows.append({"shuffle_block_bytes": size, "streams": n,
+        rows.append({"shuffle_block_bytes": size, "streams": n, "write_read_GBps": round(src.size / (tw + tr) / 1e6, 2),
                      "gpu_encode_GBps": round(src.size / tw / 1e6, 2), "gpu_encode_ratio": round(rg, 4),
                      "gpu_encode_roofline_frac": round((1 + rg) * src.size / (tw * 1e-3) / 1e9 / peak, 5),
                      "gpu_decode_libzstd3_GBps": round(src.size / tr / 1e6, 2), "libzstd3_ratio": round(rl, 4),
                      "gpu_decode_roofline_frac": round((1 + rl) * src.size / (tr * 1e-3) / 1e9 / peak, 5)})
         for p in (d_src, d_cmp, d_out, d_f):
             c.dev_free(p)
-    print(json.dumps({"config": "BASELINE config 5: zstd, shuffle-block size sweep, %d MiB per point, 1 x B200" % (total >> 20),
-                      "hbm_peak_GBps": peak, "note": "decode time includes the size pass (frames carry no content size); "
-                      "64 MiB blocks are omitted: the execute stage runs one warp per stream",
-                      "rows": rows}, indent=1))
+    doc = {"config": "BASELINE config 5: zstd level 3, shuffle-block size sweep 4 KiB .. 64 MiB, %d MiB per point, 1 x B200" % (total >> 20),
+           "hbm_peak_GBps": peak, "note": "decode time includes the size pass (frames carry no content size); the read leg "
+           "decodes frames written by libzstd level 3 (what zstd-jni writes), the write leg is the GPU encoder at level 3",
+           "rows": rows}
+    if "--bench-line" in sys.argv:  # bench.py --config 5: one JSON line in the bench contract's shape
+        vals = sorted(r["write_read_GBps"] for r in rows)
+        print(json.dumps({"metric": "shuffle write+read GB/s (compress+CRC) at 1/2/4/8 B200 vs JVM-LZ4 CPU baseline",
+                          "value": vals[len(vals) // 2], "unit": "GB/s", "n_gpus": 1, "steps": 1, "warmup": 1,
+                          "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": doc["config"] + " (value = median over the block sizes)", "baseline_config": 5},
+                          "sweep": doc}))
+    else:
+        print(json.dumps(doc, indent=1))
 
 
 if __name__ == "__main__":
