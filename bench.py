@@ -15,9 +15,9 @@ One "step" = one write pass (b2s_compress_*: XXH32 + match/parse/emit + framing 
 one read pass (b2s_decompress_*: CRC32C verify + decode + XXH32 verify) over the rank's whole share.
   value : uncompressed bytes / (t_write + t_read), inputs and outputs resident in HBM (device API)
   e2e   : the same through the host-pointer C ABI a JVM would call (NUMA-local pinned host arenas; H2D and D2H inside the
-          timed region).  e2e.value is the write||read figure — a map-side compress call and a reduce-side decompress call
-          in flight together from two task threads, the way an executor's task slots use the two lanes of the ABI and both
-          directions of the PCIe link; e2e.serial is one call at a time (round 1's figure)
+          timed region).  Two modes are timed: e2e.serial = one call at a time (round 1's figure), e2e.concurrent = a
+          map-side compress call and a reduce-side decompress call in flight together from two task threads (one per lane
+          of the ABI, both directions of the PCIe link).  e2e.value is the faster of the two and e2e.mode names it
   roofline : dominant kernel algorithmic bytes (1+r)*U per launch / CUDA-event duration vs measured HBM peak
   cpu_baseline : the reference's CPU arithmetic (liblz4 / libzstd / restated snappy + framing + XXH32 + CRC32C, oracle/), all
                  host cores the cgroup grants, bounded sample of the same data
@@ -36,12 +36,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware work queue per stream of the library's two lanes (read at CUDA context creation, which torch / NCCL may do
+# before b2s_init gets the chance: csrc/api.cu, b2s_init)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 RECORD = 104
 LZ4_BLOCK = 32768
-# ncu --set full of one lz4_match2_kernel launch over 32,768 codec blocks: dram__bytes_read 1.564 GB + dram__bytes_write
-# 2.060 GB (profiles/r2_match_parse.md); scaled to the blocks one launch of this run processes
-NCU_TRAFFIC_PER_CODEC_BLOCK = (1.564307e9 + 2.059700e9) / 32768
+# ncu --set full, one launch over 32,768 codec blocks, dram__bytes_read + dram__bytes_write; scaled to the blocks one launch
+# of this run processes.  Default pipeline (lz4_match_kernel<12>): profiles/r2z_final.md; B2S_LZ4_PIPE=4
+# (lz4_match2_kernel<12>): profiles/r2_compress_generations.md
+NCU_TRAFFIC_PER_CODEC_BLOCK = {1: (1.944139e9 + 4.139978e9) / 32768, 4: (1.564307e9 + 2.059700e9) / 32768}
 METRIC = "shuffle write+read GB/s (compress+CRC) at 1/2/4/8 B200 vs JVM-LZ4 CPU baseline"
 WAVE_BLOCKS_SMALL = 200000   # 65,520-B blocks per resident wave (13.1 GB)
 WAVE_BLOCKS_LARGE = 20000    # 671,112-B blocks per resident wave (13.4 GB)
@@ -361,7 +365,7 @@ def main():
     match_launches = max(1, int(statistics.mean(kt["match_launches"])))
     dec_ms = statistics.mean(kt["decompress_ms"])
     peak, peak_src = measured_peak()
-    pipe = int(os.environ.get("B2S_LZ4_PIPE", "2"))
+    pipe = int(os.environ.get("B2S_LZ4_PIPE", "1"))
     dom_kernel = "lz4_match2_kernel<12>" if pipe != 1 else "lz4_match_kernel<12>"
     # dominant kernel = the match kernel (phase A of the compressor; largest share in profiles/*launches*.csv).
     # achieved = SURVEY §8(d)'s write-step figure (1+r) x the input bytes one launch processes / its launch duration.
@@ -371,7 +375,8 @@ def main():
     codec_blocks_per_launch = n * -(-block_bytes // LZ4_BLOCK) / match_launches
     roofline = {"bound": "hbm", "kernel": dom_kernel, "achieved": round(achieved, 2), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 5),
-                "traffic": int(NCU_TRAFFIC_PER_CODEC_BLOCK * codec_blocks_per_launch) if pipe != 1 else None,
+                "traffic": (int(NCU_TRAFFIC_PER_CODEC_BLOCK[pipe] * codec_blocks_per_launch)
+                            if pipe in NCU_TRAFFIC_PER_CODEC_BLOCK and codec_name == "lz4" else None),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(match_ms / match_launches, 4),
                 "launches_per_wave": match_launches,
@@ -492,16 +497,22 @@ def main():
                 raise RuntimeError("concurrent e2e leg failed: %s" % errs)
             c_val = world * rank_bytes / (c_elapsed / args.e2e_steps) / 1e9
             tw2, tr2 = tms["w"], tms["r"]
-            e2e = {"value": round(c_val, 3), "unit": "GB/s", "mode": "write || read: a compress call and a decompress call in "
-                   "flight together from two task threads (one per ABI lane), each over the rank's whole share per step",
+            concurrent = {"value": round(c_val, 3), "ms_per_step": round(c_elapsed / args.e2e_steps * 1e3, 2),
+                          "write_ms": round(tw2["total_ms"], 2), "read_ms": round(tr2["total_ms"], 2),
+                          "write_sums_ms": {k: round(tw2[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
+                          "read_sums_ms": {k: round(tr2[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")}}
+            # headline = the faster of the two ways of driving the ABI, named (the two lanes remove the lock,
+            # but one FIFO copy queue per direction keeps the duplex gain away for now)
+            best_serial = s_val >= c_val
+            e2e = {"value": round(max(s_val, c_val), 3), "unit": "GB/s",
+                   "mode": ("serial: one C-ABI call at a time (write pass, then read pass)" if best_serial else
+                            "write || read: a compress call and a decompress call in flight together from two task "
+                            "threads (one per ABI lane)"),
                    "h2d_bytes_per_step": int((tw2["h2d_bytes"] + tr2["h2d_bytes"]) * waves),
                    "d2h_bytes_per_step": int((tw2["d2h_bytes"] + tr2["d2h_bytes"]) * waves),
-                   "ms_per_step": round(c_elapsed / args.e2e_steps * 1e3, 2), "steps": args.e2e_steps,
-                   "blocks_per_gpu": n * waves, "numa_node": numa_node, "process_bound_to_node": early_numa,
-                   "write_ms": round(tw2["total_ms"], 2), "read_ms": round(tr2["total_ms"], 2),
-                   "write_sums_ms": {k: round(tw2[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
-                   "read_sums_ms": {k: round(tr2[k], 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
-                   "serial": serial,
+                   "ms_per_step": round((s_elapsed if best_serial else c_elapsed) / args.e2e_steps * 1e3, 2),
+                   "steps": args.e2e_steps, "blocks_per_gpu": n * waves, "numa_node": numa_node,
+                   "process_bound_to_node": early_numa, "serial": serial, "concurrent": concurrent,
                    "api": "b2s_compress_packed + b2s_decompress_packed on NUMA-local pinned host arenas (b2s_host_alloc)"}
             if world == 1 and n >= 200:
                 # what ONE Spark task hands over: a map task's 200 partitions (commitAllPartitions), a reduce task's

@@ -32,7 +32,7 @@ def _nvcc():
 
 
 def _deps_mtime():
-    m = 0.0
+    m = os.path.getmtime(os.path.abspath(__file__))  # the source list lives here
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in os.listdir(root):
             if f.endswith((".cu", ".cuh", ".h")):

@@ -62,7 +62,7 @@ int g_trace = 0;  // B2S_TRACE=1: per-chunk timeline of the compress pipeline on
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int g_read_priority = 1;       // B2S_READ_PRIORITY=0: both lanes at the default stream priority
-int g_read_lag = 2;            // B2S_READ_LAG: chunks between the stages of the read pipeline (upload+sizes | decode | download)
+int g_read_lag = 1;            // B2S_READ_LAG: chunks between the stages of the read pipeline (upload+sizes | decode | download)
 int g_overlap = 1;             // B2S_OVERLAP=0: match / token kernels on the main stream (no two-stream overlap); A/B runs
 uint64_t g_copy_piece = 0;     // B2S_COPY_PIECE_MB: host<->device payload copies are issued in pieces of this size so the
                                // copy engines interleave the two lanes' transfers instead of draining one lane's queue
@@ -429,16 +429,17 @@ int compress_enqueue(Context* C, Slot& S, const ChecksumTables& tabs, uint32_t b
   CU(cudaMemsetAsync(J.d_down, 0, J.down_bytes, st));
   CU(cudaEventRecord(S.ev_k0, st));
   const uint32_t codec = J.codec;
-  if (codec == B2S_CODEC_LZ4BLOCK)
-    launch_xxh32_encode(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, kXxhSeed, M.hash, st, launches);
   CU(cudaEventRecord(S.ev_t0, st));
-  CU(cudaMemsetAsync(M.total, 0, 16, st));
   // Chunks of `chunk` codec blocks.  The match kernel (issue bound, shared-memory limited) of chunk k+1 runs on the
   // side stream while parse (latency bound, one thread per block), scan and emit of chunk k run on the main stream;
-  // the two workspaces alternate.
+  // the two workspaces alternate.  The side stream forks BEFORE the per-block XXH32 pass (LZ4Block headers; only the
+  // emit kernel needs it), so that pass runs beside the first chunk's match kernel instead of in front of it.
   cudaStream_t side = g_overlap ? S.st2 : st;
   CU(cudaEventRecord(S.ev_fork, st));
   CU(cudaStreamWaitEvent(side, S.ev_fork, 0));
+  if (codec == B2S_CODEC_LZ4BLOCK)
+    launch_xxh32_encode(d_src, M.src_off, M.src_len, M.blk_base, n, nb, bs, kXxhSeed, M.hash, st, launches);
+  CU(cudaMemsetAsync(M.total, 0, 16, st));
   uint32_t k = 0;
   for (uint32_t b0 = 0; b0 < nb; b0 += chunk, k++) {
     const uint32_t m = std::min<uint32_t>(chunk, nb - b0);
@@ -715,6 +716,9 @@ int decompress_enqueue_b(Slot& S, DecompressJob& J, const uint8_t* d_src, uint8_
     launch_lz4_decompress(desc, (uint32_t)J.nb, d_src, d_dst, J.status, J.counter, st, launches);
   }
   CU(cudaEventRecord(S.ev_t1, st));
+  // One XXH32 pass over all decoded blocks after the last chunk.  Queueing it chunk by chunk on the side stream (beside
+  // the next chunk's copy kernel) was measured: the read pass went from 64.3 to 71.2 ms per 10 GiB — both kernels are
+  // memory-latency bound and take each other's L2 / DRAM queue slots (profiles/r2z_final.md).
   if (J.codec == B2S_CODEC_LZ4BLOCK)
     launch_xxh32_verify(desc, (uint32_t)J.nb, d_dst, kXxhSeed, 0x0FFFFFFFu, J.status, st, launches);
   CU(cudaEventRecord(S.ev_k1, st));
@@ -878,6 +882,17 @@ const char* b2s_last_error(void) { return t_last_error.c_str(); }
 int b2s_init(uint32_t gpu_mask, uint64_t pinned_bytes_per_gpu, uint32_t streams_per_gpu) {
   std::lock_guard<std::mutex> lk(g_init_mtx);
   if (g_ctx) return 0;
+  // Hardware work queues.  A device runs 2 lanes x B2S_SLOTS slots x 2 streams (24 by default); CUDA multiplexes streams
+  // onto CUDA_DEVICE_MAX_CONNECTIONS queues (8 unless set) and streams that share a queue run in submission order — the
+  // read lane's uploads then wait behind whole chunks of the write lane.  Measured (profiles/r2z_final.md): a write call
+  // and a read call in flight together take 460 ms per 10 GiB step with the driver's default, 399 ms with 32.  The
+  // variable is read when the CUDA context is created, so it only helps if the library gets here first (a host that
+  // creates the context earlier sets it itself: bench.py does); an explicit setting is never overridden.
+  if (env_int("B2S_MAX_CONNECTIONS", 32) > 0 && !getenv("CUDA_DEVICE_MAX_CONNECTIONS")) {
+    char v[16];
+    snprintf(v, sizeof v, "%d", std::min(32, env_int("B2S_MAX_CONNECTIONS", 32)));
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", v, 0);
+  }
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0)
@@ -1337,7 +1352,8 @@ static int compress_host(uint32_t codec, int32_t level, uint32_t codec_block_siz
         t_timing.d2h_bytes += fit;
       } else {
         for (uint32_t k = 0; k < J.n; k++) dst_off[i0 + k] = run_off + J.h_dst_off[k];
-        if (chunk_total) CU(copy_async(packed_dst + run_off, S.dst.p, chunk_total, cudaMemcpyDeviceToHost, S.st));
+        if (chunk_total)
+          CU(copy_async(packed_dst + run_off, S.dst.p, chunk_total, cudaMemcpyDeviceToHost, S.st));
         t_timing.d2h_bytes += chunk_total;
       }
       run_off += chunk_total;
