@@ -137,6 +137,9 @@ void launch_zstd_execute(const uint8_t* src_base, const void* d_blocks, const ui
 int zstd_ctables_create(void** d_tables);  // predefined FSE compression tables, on the current device
 void zstd_ctables_destroy(void* d_tables);
 void zstd_set_ctables(int ordinal, const void* d_tables);
+// per-block scratch of the Zstandard entropy stage: 192 bytes of sequence-section header (modes + table descriptions,
+// zstdenc::kSeqHeaderMax) + one byte per position + 32 for the bitstream
+inline size_t zstd_bits_stride(size_t stride) { return stride + 32 + 192; }
 void launch_zstd_seqenc(const uint8_t* src_base, const uint64_t* d_src_off, const uint64_t* d_src_len,
                         const uint32_t* d_blk_base, uint32_t n_streams, uint32_t b0, uint32_t m, uint32_t block_size,
                         uint32_t stride, uint32_t max_seq, const uint16_t* d_off, const uint2* d_seq,

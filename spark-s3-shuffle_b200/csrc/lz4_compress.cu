@@ -948,7 +948,7 @@ static void launch_match2_t(const uint8_t* src_base, const uint64_t* d_src_off, 
 //   off   u16 per position                                     (all)
 //   aux   generation 1: ml u16 per position; generation >= 2: one 32-bit match mask per window
 //   seq   8-byte records, max_seq per block                     (all)
-//   bits  one byte per position + 32: the sequence bitstream    (Zstandard only)
+//   bits  zstd_bits_stride(): sequence-section header + bitstream (Zstandard only)
 struct Lz4Ws {
   uint32_t stride, max_seq;
   uint16_t *off, *ml;
@@ -965,7 +965,7 @@ size_t lz4_compress_ws_bytes(uint32_t chunk_blocks, uint32_t block_size, uint32_
   const size_t stride = (block_size + 31u) & ~31u;
   const int pipe = pipe_for(codec);
   const size_t per_block = stride * 2 + ws_aux_bytes(stride, pipe) + ws_max_seq(stride, pipe) * 8 +
-                           (codec == B2S_CODEC_ZSTD ? stride + 32 : 0);
+                           (codec == B2S_CODEC_ZSTD ? zstd_bits_stride(stride) : 0);
   return (size_t)chunk_blocks * per_block + 1024;
 }
 static Lz4Ws carve_ws(uint8_t* d_ws, uint32_t m, uint32_t block_size, uint32_t codec) {

@@ -3,12 +3,14 @@
 // Replaces com.github.luben.zstd.ZstdOutputStreamNoFinalizer [U] (zstd-jni -> libzstd ZSTD_compressStream2) under
 // SerializerManager.wrapStream on the streams of shuffle/S3ShuffleMapOutputWriter.scala:140-146 for
 // spark.io.compression.codec=zstd.  Staged encoder: valid frames first — the shared LZ match finder and
-// greedy parse (lz4_match_kernel, lz4_parse_kernel<2>), Raw_Literals + predefined-FSE sequences, Raw_Block fallback;
-// Huffman literals and block-adaptive FSE tables (the rest of level 1..3's ratio) are the follow-up.
+// greedy parse (lz4_match_kernel, lz4_parse_kernel<2>), Raw_Literals + FSE sequences with the block's own tables where
+// they pay (zstd_enc_core.h: histogram -> normalised counts -> table description + coding tables, per thread),
+// Raw_Block fallback.  Huffman literals are the follow-up (worth nothing on terasort keys, ~20 % on text).
 //   stream = frame header (6 B: magic, descriptor, 128 KiB window) | one block per codec block | empty last Raw_Block
 //
-//   zstd_seqenc_kernel  THREAD per block: the sequence bitstream is a serial state machine (three interleaved FSE
-//                       states, written in reverse sequence order) -> per-block scratch, decides Raw vs Compressed
+//   zstd_seqenc_kernel  THREAD per block: code histograms, the block's own FSE tables (thread-private, 1.6 KB), then the
+//                       sequence bitstream — a serial state machine (three interleaved FSE states, written in reverse
+//                       sequence order) -> per-block scratch [modes + table descriptions | bitstream], Raw vs Compressed
 //   zstd_emit_kernel    warp per block, lane per sequence: block + section headers, gathers the literals, moves the
 //                       bitstream to its final packed position
 // CPU model with identical output: tests/native/zstd_core_host.cpp::zc_compress_model.
@@ -18,6 +20,8 @@
 namespace b2s {
 
 using zstdenc::CTables;
+using zstdenc::kSeqHeaderMax;
+static_assert(zstdenc::kSeqHeaderMax == 192, "zstd_bits_stride() in kernels.h reserves 192 bytes for the header");
 
 __device__ __forceinline__ uint32_t find_stream_z(const uint32_t* __restrict__ blk_base, uint32_t n_streams, uint32_t b) {
   uint32_t lo = 0, hi = n_streams;
@@ -27,6 +31,41 @@ __device__ __forceinline__ uint32_t find_stream_z(const uint32_t* __restrict__ b
   }
   return lo;
 }
+
+// Sequence i of a block as the encoder core wants it, read from the parse records and the off[] table.  The core walks
+// the sequences strictly in order (forwards for the histograms, backwards for the bitstream); a record load and the
+// dependent off[] gather are two trips to L2/DRAM, and issued on demand they were the whole kernel: ~2,800 cycles per
+// sequence, 12.7 ms per 32,768 blocks wherever the tables lived (profiles/r2z_zstd.md).  The reader keeps six records and
+// three offsets in flight in registers, i.e. every load is issued three to six sequences before its use.
+struct SeqReader {
+  const uint2* __restrict__ seq;
+  const uint16_t* __restrict__ offp;
+  uint32_t omask;
+  int n, next, dir;
+  uint2 r0, r1, r2, r3, r4, r5;
+  uint32_t o0, o1, o2;
+  __device__ __forceinline__ uint2 rec(int i) const { return seq[i < 0 ? 0 : (i >= n ? n - 1 : i)]; }
+  __device__ __forceinline__ uint32_t off_of(const uint2 r) const { return offp[(r.x & 0xffffu) + (r.x >> 16)] & omask; }
+  __device__ __forceinline__ void start(int i, int d) {
+    next = i;
+    dir = d;
+    r0 = rec(i); r1 = rec(i + d); r2 = rec(i + 2 * d); r3 = rec(i + 3 * d); r4 = rec(i + 4 * d); r5 = rec(i + 5 * d);
+    o0 = off_of(r0); o1 = off_of(r1); o2 = off_of(r2);
+  }
+  __device__ __forceinline__ zstdenc::Seq operator()(uint32_t i) {
+    if ((int)i != next) start((int)i, i == 0 ? 1 : -1);
+    zstdenc::Seq q;
+    q.ll = r0.x >> 16;
+    q.ml = r0.y & 0xffffu;
+    q.off = o0;
+    r0 = r1; r1 = r2; r2 = r3; r3 = r4; r4 = r5;
+    r5 = rec(next + 6 * dir);
+    o0 = o1; o1 = o2;
+    o2 = off_of(r2);
+    next += dir;
+    return q;
+  }
+};
 
 // records from lz4_parse_kernel<2>: x = literal start | literal count << 16 ; y = match length | literal position << 16
 __global__ void __launch_bounds__(64) zstd_seqenc_kernel(
@@ -48,23 +87,25 @@ __global__ void __launch_bounds__(64) zstd_seqenc_kernel(
   const uint32_t total_lit = (tail.y >> 16) + (tail.x >> 16);
   const uint32_t nreal = ns - 1;
   bool raw = nreal == 0;
-  uint32_t nb = 0, cs = 0;
+  uint32_t nb = 0, cs = 0, hb = 0;
   if (!raw) {
-    nb = zstdenc::encode_sequences(
-        T, nreal,
-        [&](uint32_t i) {
-          const uint2 r = seq[i];
-          zstdenc::Seq q;
-          q.ll = r.x >> 16;
-          q.ml = r.y & 0xffffu;
-          q.off = offp[(r.x & 0xffffu) + q.ll] & (stride <= 32768u ? 0x7fffu : 0xffffu);  // bit 15: parse flag (lz4_compress.cu)
-          return q;
-        },
-        bits + (size_t)bl * bits_stride, n);
-    cs = zstdenc::raw_literals_header_bytes(total_lit) + total_lit + zstdenc::nseq_header_bytes(nreal) + 1 + nb;
+    // The block's own coding tables are thread-private (local memory, 1.6 KB).  One BlockTables per thread in shared
+    // memory was measured too: 2 CTAs of 64 threads per SM instead of 8, compress step 401 vs 207 ms per 10 GiB — this
+    // kernel lives on occupancy (profiles/r2z_zstd.md).
+    zstdenc::BlockTables local_tables;
+    zstdenc::BlockTables* B = &local_tables;
+    uint8_t* scratch = bits + (size_t)bl * bits_stride;
+    SeqReader get;
+    get.seq = seq;
+    get.offp = offp;
+    get.omask = stride <= 32768u ? 0x7fffu : 0xffffu;  // bit 15: parse flag (lz4_compress.cu)
+    get.n = (int)nreal;
+    get.next = -1;
+    nb = zstdenc::encode_block_sequences(T, B, nreal, get, scratch, &hb, scratch + kSeqHeaderMax, n);
+    cs = zstdenc::raw_literals_header_bytes(total_lit) + total_lit + zstdenc::nseq_header_bytes(nreal) + hb + nb;
     if (nb > n || cs >= n) raw = true;
   }
-  nbits_out[b] = nb;
+  nbits_out[b] = nb | (hb << 20);  // nb <= 2^16, hb <= kSeqHeaderMax
   csize[b] = raw ? (n | 0x80000000u) : cs;
   sizes[b] = 3u + (uint64_t)(raw ? n : cs);
 }
@@ -129,11 +170,12 @@ __global__ void __launch_bounds__(kZEmitThreads) zstd_emit_kernel(
   uint8_t* __restrict__ q = lits + total_lit;
   const uint32_t nreal = ns - 1;
   const uint32_t hb = zstdenc::nseq_header_bytes(nreal);
-  if (lane == 0) {
-    zstdenc::put_nseq(q, nreal);
-    q[hb] = 0;  // predefined literal-length / offset / match-length distributions
-  }
-  group_copy<32>(q + hb + 1, bits + (size_t)bl * bits_stride, nbits[b], lane);
+  if (lane == 0) zstdenc::put_nseq(q, nreal);
+  // Compression_Modes + the block's own table descriptions, then the bitstream (zstd_seqenc_kernel's scratch layout)
+  const uint8_t* __restrict__ scratch = bits + (size_t)bl * bits_stride;
+  const uint32_t packed = nbits[b], nbs = packed & 0xfffffu, th = packed >> 20;
+  for (uint32_t j = lane; j < th; j += 32) q[hb + j] = scratch[j];
+  group_copy<32>(q + hb + th, scratch + kSeqHeaderMax, nbs, lane);
 }
 
 // per stream: frame header at the start, empty last Raw_Block at the end, packed offset/length, capacity check
@@ -186,8 +228,8 @@ void launch_zstd_seqenc(const uint8_t* src_base, const uint64_t* d_src_off, cons
   int dev = 0;
   cudaGetDevice(&dev);
   zstd_seqenc_kernel<<<(m + 63) / 64, 64, 0, st>>>(d_src_len, d_blk_base, n_streams, b0, m, block_size, stride, max_seq,
-                                                  stride + 32, d_off, d_seq, d_nseq, g_ctables_for_device[dev & 63],
-                                                  d_bits, d_nbits, d_csize, d_sizes);
+                                                  (uint32_t)zstd_bits_stride(stride), d_off, d_seq, d_nseq,
+                                                  g_ctables_for_device[dev & 63], d_bits, d_nbits, d_csize, d_sizes);
   *launches += 1;
 }
 
@@ -198,7 +240,8 @@ void launch_zstd_emit(const uint8_t* src_base, const uint64_t* d_src_off, const 
                       uint8_t* dst_base, uint64_t dst_cap, cudaStream_t st, uint64_t* launches) {
   if (!m) return;
   zstd_emit_kernel<<<(m + kZEmitThreads / 32 - 1) / (kZEmitThreads / 32), kZEmitThreads, 0, st>>>(
-      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, max_seq, stride + 32, d_seq, d_nseq,
+      src_base, d_src_off, d_src_len, d_blk_base, n_streams, b0, m, block_size, max_seq, (uint32_t)zstd_bits_stride(stride),
+      d_seq, d_nseq,
       d_bits, d_nbits, d_csize, d_scan, dst_base, dst_cap);
   *launches += 1;
 }

@@ -153,13 +153,16 @@ extern "C" long long zc_compress_model_hlog(const unsigned char* src, unsigned l
       }
     }
     lits.insert(lits.end(), s + anchor, s + bn);
-    // compressed block: raw literals + predefined-FSE sequences, when smaller than the raw block
+    // compressed block: raw literals + FSE sequences (own or predefined tables), when smaller than the raw block
     bool raw = seqs.empty();
-    uint32_t csize = 0, nbits = 0;
+    uint32_t csize = 0, nbits = 0, hb = 0;
+    uint8_t hdr[kSeqHeaderMax];
     if (!raw) {
       bits.assign((size_t)bn + 16, 0);
-      nbits = encode_sequences(&T, (uint32_t)seqs.size(), [&](uint32_t i) { return seqs[i]; }, bits.data(), (uint32_t)bn);
-      csize = raw_literals_header_bytes((uint32_t)lits.size()) + (uint32_t)lits.size() + nseq_header_bytes((uint32_t)seqs.size()) + 1 + nbits;
+      BlockTables B;
+      nbits = encode_block_sequences(&T, &B, (uint32_t)seqs.size(), [&](uint32_t i) { return seqs[i]; }, hdr, &hb,
+                                     bits.data(), (uint32_t)bn);
+      csize = raw_literals_header_bytes((uint32_t)lits.size()) + (uint32_t)lits.size() + nseq_header_bytes((uint32_t)seqs.size()) + hb + nbits;
       if (nbits > (uint32_t)bn || csize >= (uint32_t)bn) raw = true;
     }
     const uint32_t payload = raw ? (uint32_t)bn : csize;
@@ -176,7 +179,8 @@ extern "C" long long zc_compress_model_hlog(const unsigned char* src, unsigned l
       q += lits.size();
       put_nseq(q, (uint32_t)seqs.size());
       q += nseq_header_bytes((uint32_t)seqs.size());
-      *q++ = 0;  // predefined LL / OF / ML
+      memcpy(q, hdr, hb);  // Compression_Modes + the block's own table descriptions
+      q += hb;
       memcpy(q, bits.data(), nbits);
     }
     op += payload;
@@ -184,4 +188,24 @@ extern "C" long long zc_compress_model_hlog(const unsigned char* src, unsigned l
   put_block_header(dst + op, 1, 0, 0);  // empty Raw_Block with Last_Block
   op += kEndBlockBytes;
   return (long long)op;
+}
+
+// ---- the per-block FSE table helpers of zstd_enc_core.h, exposed for property tests ---------------------------------
+extern "C" void zc_normalize(const uint16_t* cnt, int nsym, unsigned total, int log, int16_t* norm) {
+  b2s::zstdenc::normalize_counts(cnt, nsym, total, log, norm);
+}
+// writes the description of norm[0..nsym) (norm[nsym] must be addressable: the sentinel) and reads it back with the
+// DECODER's header reader; returns the description's bytes, or -1 when the round trip differs
+extern "C" int zc_ncount_roundtrip(int16_t* norm, int nsym, int log, int max_sym, int max_log) {
+  uint8_t buf[256];
+  norm[nsym] = 1;
+  const uint32_t n = b2s::zstdenc::write_ncount(buf, norm, log);
+  int16_t back[64];
+  for (int i = 0; i < 64; i++) back[i] = 0;
+  int log2 = 0, nsym2 = 0;
+  const uint64_t used = b2s::zstd::fse_read_header(buf, n, back, max_sym, max_log, &log2, &nsym2);
+  if (used != n || log2 != log) return -1;
+  for (int s = 0; s < nsym; s++)
+    if ((s < nsym2 ? back[s] : 0) != norm[s]) return -1;
+  return (int)n;
 }

@@ -143,8 +143,9 @@ def test_mutated_frames_never_crash_and_both_decoders_agree(zc, oracle):
 
 
 def test_encoder_model_frames_are_read_by_libzstd(zc, oracle):
-    """zstd_enc_core.h (raw literals + predefined-FSE sequences) through the CPU model of the GPU encoder: libzstd and
-    our own decoder core both reproduce the input; incompressible blocks fall back to Raw_Block."""
+    """zstd_enc_core.h (raw literals + FSE sequences with the block's own or the predefined tables) through the CPU model
+    of the GPU encoder: libzstd and our own decoder core both reproduce the input; incompressible blocks fall back to
+    Raw_Block."""
     zc.zc_compress_model.restype = C.c_longlong
     zc.zc_compress_model.argtypes = [C.c_char_p, C.c_ulonglong, C.c_uint, C.c_char_p, C.c_ulonglong]
     for kind in KINDS:
@@ -196,3 +197,53 @@ def test_committed_libzstd_frames(zc):
             assert zc.zc_size(f, len(f)) == c["input_len"]
             n += 1
     assert n == 40
+
+
+def test_block_tables_normalisation_and_description_round_trip(zc):
+    """normalize_counts: probabilities sum to 1 << log and every symbol that occurs keeps >= 1; write_ncount: the table
+    description is read back by the decoder's fse_read_header (and, inside frames, by libzstd — the test above)"""
+    import random
+    rng = random.Random(5)
+    zc.zc_normalize.argtypes = [C.POINTER(C.c_uint16), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_int16)]
+    zc.zc_ncount_roundtrip.argtypes = [C.POINTER(C.c_int16), C.c_int, C.c_int, C.c_int, C.c_int]
+    for nsym, max_sym, log, max_log in ((36, 35, 7, 9), (32, 31, 6, 8), (53, 52, 7, 9), (36, 35, 9, 9), (53, 52, 6, 9)):
+        for trial in range(300):
+            present = rng.sample(range(nsym), rng.randint(2, min(nsym, 1 << log)))
+            cnt = [0] * nsym
+            shape = trial % 4
+            for s in present:
+                cnt[s] = (1 if shape == 0 else rng.randint(1, 8000) if shape == 1 else
+                          int(8000 * rng.random() ** 6) + 1 if shape == 2 else rng.choice((1, 1, 1, 5000)))
+            while sum(cnt) > 65535:
+                cnt = [(c + 1) // 2 if c else 0 for c in cnt]
+            arr = (C.c_uint16 * nsym)(*cnt)
+            norm = (C.c_int16 * (nsym + 1))()
+            zc.zc_normalize(arr, nsym, sum(cnt), log, norm)
+            got = list(norm)[:nsym]
+            assert sum(got) == 1 << log, (cnt, got)
+            assert all((g >= 1) == (c > 0) for g, c in zip(got, cnt)), (cnt, got)
+            n = zc.zc_ncount_roundtrip(norm, nsym, log, max_sym, max_log)
+            assert 0 < n <= 70, (cnt, got, n)
+
+
+def test_block_tables_pay_on_the_terasort_shape(zc, oracle):
+    """the reason they exist: 14 sequences per 104-byte record, whose codes cost ~12.5 bits with the predefined tables
+    and ~5 with the block's own (ratio 0.43 -> 0.30); all three tables of a full block are FSE_Compressed"""
+    zc.zc_compress_model.restype = C.c_longlong
+    zc.zc_compress_model.argtypes = [C.c_char_p, C.c_ulonglong, C.c_uint, C.c_char_p, C.c_ulonglong]
+    d = corpus(oracle, "terasort", 671112, seed=1)
+    buf = C.create_string_buffer(len(d))
+    c = zc.zc_compress_model(d, len(d), 32768, buf, len(d))
+    assert 0 < c < 0.32 * len(d)
+    f = buf.raw[:c]
+    assert zstd_ref.decompress(f) == d
+    # first block: 6-byte frame header, 3-byte block header, raw literals header, literals, nseq, modes
+    bh = int.from_bytes(f[6:9], "little")
+    assert (bh >> 1) & 3 == 2                      # Compressed_Block
+    assert f[9] & 3 == 0                           # Raw_Literals
+    fmt = (f[9] >> 2) & 3
+    hl = 1 if fmt in (0, 2) else 2 if fmt == 1 else 3
+    nlit = int.from_bytes(f[9:9 + hl], "little") >> (3 if hl == 1 else 4)
+    q = 9 + hl + nlit
+    assert f[q] >= 128                             # >= 128 sequences: two-byte count
+    assert f[q + 2] == 0b10101000                  # LL, OF, ML all FSE_Compressed_Mode
