@@ -247,3 +247,27 @@ def test_block_tables_pay_on_the_terasort_shape(zc, oracle):
     q = 9 + hl + nlit
     assert f[q] >= 128                             # >= 128 sequences: two-byte count
     assert f[q + 2] == 0b10101000                  # LL, OF, ML all FSE_Compressed_Mode
+
+
+def test_encoder_model_fuzz_mixed_streams_decode_with_libzstd(zc, oracle):
+    """mixed corpora, tiny alphabets, long periodic runs, odd block sizes, all three match-table sizes: every frame the
+    encoder model writes (any mix of own / predefined tables per block, Raw_Block fallback) is decoded by libzstd"""
+    import random
+    rng = random.Random(11)
+    zc.zc_compress_model_hlog.restype = C.c_longlong
+    zc.zc_compress_model_hlog.argtypes = [C.c_char_p, C.c_ulonglong, C.c_uint, C.c_char_p, C.c_ulonglong, C.c_int]
+    for _ in range(120):
+        parts = [corpus(oracle, rng.choice(KINDS), rng.choice([0, 5, 13, 50, 200, 1000, 5000, 40000, 70000]),
+                        seed=rng.randint(0, 1000)) for _ in range(rng.randint(1, 3))]
+        if rng.random() < 0.4:
+            parts.append(bytes(rng.randrange(256) for _ in range(rng.randint(1, 40))) * rng.randint(1, 3000))
+        if rng.random() < 0.3:
+            a = bytes(rng.randrange(4) for _ in range(rng.randint(20, 3000)))
+            parts.append(a + bytes(rng.randrange(256) for _ in range(rng.randint(0, 50))) + a)
+        d = b"".join(parts)
+        n, bs, hlog = len(d), rng.choice([1000, 4096, 20000, 32768, 65536]), rng.choice([11, 12, 13])
+        cap = n + n // 64 + 9 + 3 * (n // bs + 2) + 64
+        buf = C.create_string_buffer(cap)
+        c = zc.zc_compress_model_hlog(d, n, bs, buf, cap, hlog)
+        assert 9 <= c <= cap
+        assert zstd_ref.decompress(buf.raw[:c]) == d
